@@ -1,0 +1,759 @@
+// Bandwidth-bound kernels of the U-Net path (everything that is not a tensor-core contraction):
+// input packing, GroupNorm finalize/apply/backward, trilinear x2 up-sampling fwd/bwd, 1x1x1 head fwd/bwd,
+// weight packing and zero insertion.  All activations are NDHWC bf16 (hi [+ lo]) views; 8 channels (16 B) per
+// thread so every access is a 128-bit vector along the innermost (channel) axis.
+//
+// Reference semantics restated (paths relative to /root/reference):
+//   GroupNorm+ReLU      unet3d/models/pytorch/classification/myronenko.py:17-31
+//   trilinear x2        unet3d/models/pytorch/classification/decoder.py:105-106
+//   final 1x1x1 conv    unet3d/models/pytorch/autoencoder/variational.py:59-60,84
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ void load8(const bf16* hi, const bf16* lo, long long off, float (&v)[8]) {
+  uint4 a = *reinterpret_cast<const uint4*>(hi + off);
+  v[0] = bf16_lo_to_f(a.x); v[1] = bf16_hi_to_f(a.x);
+  v[2] = bf16_lo_to_f(a.y); v[3] = bf16_hi_to_f(a.y);
+  v[4] = bf16_lo_to_f(a.z); v[5] = bf16_hi_to_f(a.z);
+  v[6] = bf16_lo_to_f(a.w); v[7] = bf16_hi_to_f(a.w);
+  if (lo) {
+    uint4 b = *reinterpret_cast<const uint4*>(lo + off);
+    v[0] += bf16_lo_to_f(b.x); v[1] += bf16_hi_to_f(b.x);
+    v[2] += bf16_lo_to_f(b.y); v[3] += bf16_hi_to_f(b.y);
+    v[4] += bf16_lo_to_f(b.z); v[5] += bf16_hi_to_f(b.z);
+    v[6] += bf16_lo_to_f(b.w); v[7] += bf16_hi_to_f(b.w);
+  }
+}
+
+__device__ __forceinline__ void store8(bf16* hi, bf16* lo, long long off, const float (&v)[8]) {
+  uint4 a;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(hi + off) = a;
+  if (lo) {
+    uint4 b;
+    b.x = pack_bf16x2(v[0] - bf16_lo_to_f(a.x), v[1] - bf16_hi_to_f(a.x));
+    b.y = pack_bf16x2(v[2] - bf16_lo_to_f(a.y), v[3] - bf16_hi_to_f(a.y));
+    b.z = pack_bf16x2(v[4] - bf16_lo_to_f(a.z), v[5] - bf16_hi_to_f(a.z));
+    b.w = pack_bf16x2(v[6] - bf16_lo_to_f(a.w), v[7] - bf16_hi_to_f(a.w));
+    *reinterpret_cast<uint4*>(lo + off) = b;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ input pack
+// x: NCDHW fp32 -> out: NDHWC bf16 (C padded with zeros to out.C), + per-(n,c) sum / sum-of-squares (double).
+__global__ void k_input_pack(const float* __restrict__ x, int C, long long S, Act out, double* __restrict__ stats,
+                             int stats_ld) {
+  const int n = blockIdx.y;
+  const int Cp = out.C;  // 8 or 16
+  __shared__ float s_sum[16][2];
+  if (threadIdx.x < 32) (&s_sum[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[16][2];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c][0] = acc[c][1] = 0.f;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h * 8 < Cp) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = h * 8 + j;
+          v[j] = c < C ? x[((long long)n * C + c) * S + s] : 0.f;
+          acc[h * 8 + j][0] += v[j];
+          acc[h * 8 + j][1] += v[j] * v[j];
+        }
+        store8(out.hi, out.lo, ((long long)n * S + s) * out.ld + h * 8, v);
+      }
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < C) {
+        float a = warp_sum(acc[c][0]), b = warp_sum(acc[c][1]);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[c][0], a); atomicAdd(&s_sum[c][1], b); }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x][0]);
+      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 1], (double)s_sum[threadIdx.x][1]);
+    }
+  }
+}
+
+int launch_input_pack(const float* x, int C, const Act& out, double* stats, int stats_ld, cudaStream_t st) {
+  B200_REQUIRE(C <= 16, E_UNSUPPORTED, "input_pack: n_features=%d > 16 unsupported", C);
+  B200_REQUIRE(out.C % 8 == 0 && out.C >= C && out.C <= 16, E_INVALID, "input_pack: padded C=%d invalid", out.C);
+  long long S = (long long)out.D * out.H * out.W;
+  int threads = 256;
+  int blocks = (int)((S + threads - 1) / threads);
+  if (blocks > 1184) blocks = 1184;
+  k_input_pack<<<dim3(blocks, out.N), threads, 0, st>>>(x, C, S, out, stats, stats_ld);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ channel stats (stand-alone)
+__global__ void k_channel_stats(Act x, double* __restrict__ stats, int stats_ld) {
+  // grid (blocks, N); each thread owns one 8-channel lane group and strides over voxels
+  const int n = blockIdx.y;
+  const int c8n = x.C / 8;
+  const long long S = (long long)x.D * x.H * x.W;
+  const int lane_c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n;
+  const int vper = blockDim.x / c8n;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (vslot < vper) {
+    for (long long s = (long long)blockIdx.x * vper + vslot; s < S; s += (long long)gridDim.x * vper) {
+      float v[8];
+      load8(x.hi, x.lo, ((long long)n * S + s) * x.ld + lane_c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += v[j]; b[j] += v[j] * v[j]; }
+    }
+  }
+  extern __shared__ float sm[];  // [C][2]
+  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  if (vslot < vper) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 0], a[j]);
+      atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 1], b[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], (double)sm[i]);
+}
+
+int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t st) {
+  B200_REQUIRE(x.C % 8 == 0 && x.C <= 2048, E_INVALID, "channel_stats: C=%d", x.C);
+  long long S = (long long)x.D * x.H * x.W;
+  int threads = 256;
+  int c8n = x.C / 8;
+  if (c8n > threads) threads = round_up(c8n, 32);
+  int vper = threads / c8n;
+  long long want = (S + vper - 1) / vper;
+  int blocks = (int)(want < 296 ? want : 296);
+  k_channel_stats<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(float), st>>>(x, stats, stats_ld);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm finalize
+// stats [N][Ctot][2] (sum, sumsq over the S voxels of each channel) -> coef [N][C][4] = (A, B, mu, rstd):
+//   z = A*x + B  with A = gamma*rstd, B = beta - mu*gamma*rstd ;  xhat = (x - mu)*rstd.    (biased variance, eps)
+__global__ void k_gn_finalize(const double* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, int C, int Cld, int G, double S, float eps,
+                              float4* __restrict__ coef) {
+  // C real channels (gamma/beta length); Cld = pitch of stats/coef rows (>= C; padded channels get zero coefs)
+  const int n = blockIdx.x;
+  const int cg = C / G;
+  for (int c = threadIdx.x; c < Cld; c += blockDim.x) {
+    if (c >= C) { coef[(long long)n * Cld + c] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+    const int g = c / cg;
+    double s = 0, q = 0;
+    for (int j = 0; j < cg; ++j) {
+      s += stats[((long long)n * Cld + g * cg + j) * 2 + 0];
+      q += stats[((long long)n * Cld + g * cg + j) * 2 + 1];
+    }
+    const double m = S * cg;
+    const double mu = s / m;
+    double var = q / m - mu * mu;
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+    coef[(long long)n * Cld + c] = make_float4((float)(ga * rstd), (float)(be - mu * ga * rstd), (float)mu, (float)rstd);
+  }
+}
+
+int launch_gn_finalize(const double* stats, const float* gamma, const float* beta, int N, int C, int Cld, int G,
+                       long long S, float eps, float* coef, cudaStream_t st) {
+  B200_REQUIRE(G > 0 && C % G == 0 && Cld >= C, E_INVALID, "gn_finalize: C=%d not divisible by G=%d", C, G);
+  k_gn_finalize<<<N, 128, 0, st>>>(stats, gamma, beta, C, Cld, G, (double)S, eps, reinterpret_cast<float4*>(coef));
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm apply (+ReLU / LeakyReLU)
+__global__ void k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope) {
+  const int c8n = x.C / 8;
+  const long long S = (long long)x.D * x.H * x.W;
+  const long long total = (long long)x.N * S * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const long long vox = t / c8n;
+    const int n = (int)(vox / S);
+    float v[8];
+    load8(x.hi, x.lo, vox * x.ld + c8 * 8, v);
+    const float4* cf = coef + (long long)n * x.C + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 k = __ldg(cf + j);
+      float z = fmaf(k.x, v[j], k.y);
+      v[j] = z > 0.f ? z : z * slope;
+    }
+    store8(y.hi, y.lo, vox * y.ld + c8 * 8, v);
+  }
+}
+
+static int ew_blocks(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  long long cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st) {
+  B200_REQUIRE(x.C % 8 == 0 && y.C == x.C, E_INVALID, "gn_apply: C=%d/%d", x.C, y.C);
+  long long total = x.voxels() * (x.C / 8);
+  k_gn_apply<<<ew_blocks(total, 256), 256, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm backward
+// bstats [N][C][2] = (S1 = sum dz, S2 = sum dz*xhat) per (n,c);   dz = dL/dz (already ReLU-masked).
+// coef2 [N][C][2] = (E, F):   dx = A*dz + E*x + F      (A from coef)
+//   c1_g = (1/m) sum_{c in g} gamma_c S1_c ; c2_g = (1/m) sum gamma_c S2_c ; E = -rstd^2 c2 ; F = -rstd c1 + rstd^2 c2 mu
+// dgamma_c = sum_n S2 ; dbeta_c = sum_n S1   (written, not accumulated)
+__global__ void k_gn_bwd_finalize(const double* __restrict__ bstats, const float4* __restrict__ coef,
+                                  const float* __restrict__ gamma, int N, int C, int Cld, int G, double S,
+                                  float2* __restrict__ coef2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cg = C / G;
+  for (int c = threadIdx.x; c < Cld; c += blockDim.x) {
+    if (c >= C) {
+      for (int n = 0; n < N; ++n) coef2[(long long)n * Cld + c] = make_float2(0.f, 0.f);
+      continue;
+    }
+    const int g = c / cg;
+    double dg = 0, db = 0;
+    for (int n = 0; n < N; ++n) {
+      double c1 = 0, c2 = 0;
+      for (int j = 0; j < cg; ++j) {
+        const int cc = g * cg + j;
+        const double ga = gamma ? (double)gamma[cc] : 1.0;
+        c1 += ga * bstats[((long long)n * Cld + cc) * 2 + 0];
+        c2 += ga * bstats[((long long)n * Cld + cc) * 2 + 1];
+      }
+      const double m = S * cg;
+      c1 /= m; c2 /= m;
+      const float4 k = coef[(long long)n * Cld + c];
+      const double mu = k.z, rstd = k.w;
+      coef2[(long long)n * Cld + c] = make_float2((float)(-rstd * rstd * c2), (float)(-rstd * c1 + rstd * rstd * c2 * mu));
+      db += bstats[((long long)n * Cld + c) * 2 + 0];
+      dg += bstats[((long long)n * Cld + c) * 2 + 1];
+    }
+    if (dgamma) dgamma[c] = (float)dg;
+    if (dbeta) dbeta[c] = (float)db;
+  }
+}
+
+int launch_gn_bwd_finalize(const double* bstats, const float* coef, const float* gamma, int N, int C, int Cld, int G,
+                           long long S, float* coef2, float* dgamma, float* dbeta, cudaStream_t st) {
+  B200_REQUIRE(G > 0 && C % G == 0 && Cld >= C, E_INVALID, "gn_bwd_finalize: C=%d G=%d", C, G);
+  k_gn_bwd_finalize<<<1, 256, 0, st>>>(bstats, reinterpret_cast<const float4*>(coef), gamma, N, C, Cld, G, (double)S,
+                                      reinterpret_cast<float2*>(coef2), dgamma, dbeta);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// dx = A*dz + E*x + F (+ add1) (+ add2)
+__global__ void k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef, const float2* __restrict__ coef2, Act add1,
+                         Act add2, Act dx, const float* __restrict__ scale) {
+  const int c8n = x.C / 8;
+  const long long S = (long long)x.D * x.H * x.W;
+  const long long total = (long long)x.N * S * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const long long vox = t / c8n;
+    const int n = (int)(vox / S);
+    float g[8], v[8], o[8];
+    load8(dz.hi, dz.lo, vox * dz.ld + c8 * 8, g);
+    load8(x.hi, x.lo, vox * x.ld + c8 * 8, v);
+    const float4* cf = coef + (long long)n * x.C + c8 * 8;
+    const float2* cf2 = coef2 + (long long)n * x.C + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 k = __ldg(cf + j);
+      float2 e = __ldg(cf2 + j);
+      o[j] = fmaf(k.x, g[j], fmaf(e.x, v[j], e.y));
+    }
+    if (add1.hi) {
+      float a[8];
+      load8(add1.hi, add1.lo, vox * add1.ld + c8 * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    if (add2.hi) {
+      float a[8];
+      load8(add2.hi, add2.lo, vox * add2.ld + c8 * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= __ldg(scale + (long long)n * x.C + c8 * 8 + j);
+    }
+    store8(dx.hi, dx.lo, vox * dx.ld + c8 * 8, o);
+  }
+}
+
+int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1, const Act* add2,
+                  const Act& dx, const float* scale, cudaStream_t st) {
+  B200_REQUIRE(x.C % 8 == 0 && dz.C == x.C && dx.C == x.C, E_INVALID, "gn_bwd: channel mismatch");
+  Act none = make_act(nullptr, nullptr, 0, 0, 0, 0, 0, 0);
+  long long total = x.voxels() * (x.C / 8);
+  k_gn_bwd<<<ew_blocks(total, 256), 256, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
+                                                  reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none,
+                                                  add2 ? *add2 : none, dx, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ element-wise add (y = a + b)
+__global__ void k_add(Act a, Act b, Act y) {
+  const int c8n = a.C / 8;
+  const long long total = a.voxels() * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const long long vox = t / c8n;
+    float u[8], v[8];
+    load8(a.hi, a.lo, vox * a.ld + c8 * 8, u);
+    load8(b.hi, b.lo, vox * b.ld + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] += v[j];
+    store8(y.hi, y.lo, vox * y.ld + c8 * 8, u);
+  }
+}
+
+int launch_add(const Act& a, const Act& b, const Act& y, cudaStream_t st) {
+  B200_REQUIRE(a.C % 8 == 0 && a.C == b.C && a.C == y.C, E_INVALID, "add: channel mismatch");
+  long long total = a.voxels() * (a.C / 8);
+  k_add<<<ew_blocks(total, 256), 256, 0, st>>>(a, b, y);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trilinear x2 (align_corners=False)
+// out[2k] = .25 x[clamp(k-1)] + .75 x[k] ; out[2k+1] = .75 x[k] + .25 x[clamp(k+1)]   per axis (separable).
+// Output is written into a channel slice view (concat fusion) and its per-channel statistics are accumulated.
+__device__ __forceinline__ void up_taps(int o, int n, int& i0, int& i1, float& w0, float& w1) {
+  const int k = o >> 1;
+  if (o & 1) { i0 = k; i1 = k + 1 < n ? k + 1 : n - 1; w0 = 0.75f; w1 = 0.25f; }
+  else       { i0 = k - 1 >= 0 ? k - 1 : 0; i1 = k; w0 = 0.25f; w1 = 0.75f; }
+}
+
+__global__ void k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int stats_ld) {
+  // y dims = 2 * x dims.  thread -> (output voxel, c8)
+  const int c8n = x.C / 8;
+  extern __shared__ float sm[];  // [C][2]
+  if (stats) {
+    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const int n = blockIdx.y;
+  const long long So = (long long)y.D * y.H * y.W;
+  const long long total = So * c8n;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  int my_c8 = -1;
+  // blockDim.x is a multiple of c8n so that a thread keeps the same c8 across iterations
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    my_c8 = c8;
+    long long vo = t / c8n;
+    const int ow = (int)(vo % y.W); vo /= y.W;
+    const int oh = (int)(vo % y.H);
+    const int od = (int)(vo / y.H);
+    int d0, d1, h0, h1, w0, w1; float wd0, wd1, wh0, wh1, ww0, ww1;
+    up_taps(od, x.D, d0, d1, wd0, wd1);
+    up_taps(oh, x.H, h0, h1, wh0, wh1);
+    up_taps(ow, x.W, w0, w1, ww0, ww1);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int d = (i & 4) ? d1 : d0, h = (i & 2) ? h1 : h0, w = (i & 1) ? w1 : w0;
+      const float wt = ((i & 4) ? wd1 : wd0) * ((i & 2) ? wh1 : wh0) * ((i & 1) ? ww1 : ww0);
+      float v[8];
+      load8(x.hi, x.lo, ((((long long)n * x.D + d) * x.H + h) * x.W + w) * x.ld + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(wt, v[j], o[j]);
+    }
+    store8(y.hi, y.lo, ((((long long)n * y.D + od) * y.H + oh) * y.W + ow) * y.ld + c8 * 8, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] += o[j]; b[j] += o[j] * o[j]; }
+  }
+  if (stats) {
+    if (my_c8 >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 0], a[j]);
+        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 1], b[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], (double)sm[i]);
+  }
+}
+
+int launch_upsample2x_fwd(const Act& x, const Act& y, double* stats, int stats_ld, cudaStream_t st) {
+  B200_REQUIRE(x.C % 8 == 0 && y.C == x.C, E_INVALID, "upsample: channel mismatch");
+  B200_REQUIRE(y.D == 2 * x.D && y.H == 2 * x.H && y.W == 2 * x.W, E_UNSUPPORTED,
+               "upsample: output must be exactly 2x (got %dx%dx%d -> %dx%dx%d)", x.D, x.H, x.W, y.D, y.H, y.W);
+  const int c8n = x.C / 8;
+  int threads = 256;
+  while (threads % c8n) threads += 32;
+  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "upsample: C=%d unsupported", x.C);
+  long long total = (long long)y.D * y.H * y.W * c8n;
+  int blocks = ew_blocks(total, threads);
+  // grid-stride must preserve c8 per thread: gridDim.x*blockDim.x % c8n == 0 holds since blockDim % c8n == 0
+  k_upsample2x_fwd<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(float), st>>>(x, y, stats, stats_ld);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// adjoint: dx[k] = .75 dy[2k] + .75 dy[2k+1] + .25 dy[2k-1] (k>=1) + .25 dy[2k+2] (k<=n-2) + clamp terms
+__device__ __forceinline__ int up_adj(int k, int n, int (&idx)[4], float (&w)[4]) {
+  int cnt = 0;
+  idx[cnt] = 2 * k; w[cnt] = 0.75f; ++cnt;
+  idx[cnt] = 2 * k + 1; w[cnt] = 0.75f; ++cnt;
+  if (k >= 1) { idx[cnt] = 2 * k - 1; w[cnt] = 0.25f; ++cnt; } else { w[0] += 0.25f; }            // out[0] clamps to x[0]
+  if (k + 1 <= n - 1) { idx[cnt] = 2 * k + 2; w[cnt] = 0.25f; ++cnt; } else { w[1] += 0.25f; }  // out[2n-1] clamps to x[n-1]
+  return cnt;
+}
+
+__global__ void k_upsample2x_bwd(Act dy, Act dx) {
+  const int c8n = dx.C / 8;
+  const long long total = dx.voxels() * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    long long v = t / c8n;
+    const int w = (int)(v % dx.W); v /= dx.W;
+    const int h = (int)(v % dx.H); v /= dx.H;
+    const int d = (int)(v % dx.D);
+    const int n = (int)(v / dx.D);
+    int id[4], ih[4], iw[4]; float wd[4], wh[4], ww[4];
+    const int nd = up_adj(d, dx.D, id, wd), nh = up_adj(h, dx.H, ih, wh), nw = up_adj(w, dx.W, iw, ww);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    for (int a = 0; a < nd; ++a)
+      for (int b = 0; b < nh; ++b)
+        for (int c = 0; c < nw; ++c) {
+          const float wt = wd[a] * wh[b] * ww[c];
+          float g[8];
+          load8(dy.hi, dy.lo, ((((long long)n * dy.D + id[a]) * dy.H + ih[b]) * dy.W + iw[c]) * dy.ld + c8 * 8, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(wt, g[j], o[j]);
+        }
+    store8(dx.hi, dx.lo, ((((long long)n * dx.D + d) * dx.H + h) * dx.W + w) * dx.ld + c8 * 8, o);
+  }
+}
+
+int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st) {
+  B200_REQUIRE(dx.C % 8 == 0 && dy.C == dx.C, E_INVALID, "upsample_bwd: channel mismatch");
+  B200_REQUIRE(dy.D == 2 * dx.D && dy.H == 2 * dx.H && dy.W == 2 * dx.W, E_UNSUPPORTED, "upsample_bwd: not 2x");
+  long long total = dx.voxels() * (dx.C / 8);
+  k_upsample2x_bwd<<<ew_blocks(total, 256), 256, 0, st>>>(dy, dx);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ head: 1x1x1 conv C -> n_out
+// logits NCDHW fp32 (the reference-facing layout).  One thread per voxel; weights in shared memory.
+__global__ void k_head_fwd(Act x, const float* __restrict__ w, int n_out, int act_mode, float* __restrict__ logits) {
+  extern __shared__ float sw[];  // [n_out][C]
+  for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long S = (long long)x.D * x.H * x.W;
+  const long long total = x.N * S;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(v / S);
+    const long long s = v % S;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int c0 = 0; c0 < x.C; c0 += 8) {
+      float u[8];
+      load8(x.hi, x.lo, v * x.ld + c0, u);
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < n_out) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o] = fmaf(sw[o * x.C + c0 + j], u[j], acc[o]);
+        }
+    }
+    if (act_mode == 2) {  // softmax over channels
+      float m = -INFINITY;
+      for (int o = 0; o < n_out; ++o) m = fmaxf(m, acc[o]);
+      float z = 0.f;
+      for (int o = 0; o < n_out; ++o) { acc[o] = __expf(acc[o] - m); z += acc[o]; }
+      for (int o = 0; o < n_out; ++o) acc[o] /= z;
+    }
+    for (int o = 0; o < n_out; ++o) {
+      float r = acc[o];
+      if (act_mode == 1) r = 1.f / (1.f + __expf(-r));
+      logits[((long long)n * n_out + o) * S + s] = r;
+    }
+  }
+}
+
+int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st) {
+  B200_REQUIRE(n_out >= 1 && n_out <= 8, E_UNSUPPORTED, "head: n_outputs=%d > 8 unsupported", n_out);
+  B200_REQUIRE(x.C % 8 == 0, E_INVALID, "head: C=%d", x.C);
+  k_head_fwd<<<ew_blocks(x.voxels(), 256), 256, n_out * x.C * sizeof(float), st>>>(x, w, n_out, act_mode, logits);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// dx[v][c] = sum_o dlogits[n][o][s] * w[o][c] ;  dw[o][c] += sum_v dlogits[o] * x[v][c]
+__global__ void k_head_bwd(Act x, const float* __restrict__ w, int n_out, const float* __restrict__ dlogits, Act dx,
+                           float* __restrict__ dw) {
+  extern __shared__ float sm[];  // sw [n_out][C] | sdw [n_out][C]
+  float* sw = sm;
+  float* sdw = sm + n_out * x.C;
+  for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  __syncthreads();
+  const long long S = (long long)x.D * x.H * x.W;
+  const long long total = x.N * S;
+  const int lane = threadIdx.x & 31;
+  for (long long v0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); v0 < total;
+       v0 += (long long)gridDim.x * blockDim.x) {
+    const long long v = v0 + lane;
+    const bool ok = v < total;
+    float g[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) g[o] = 0.f;
+    if (ok) {
+      const int n = (int)(v / S);
+      const long long s = v % S;
+      for (int o = 0; o < n_out; ++o) g[o] = dlogits[((long long)n * n_out + o) * S + s];
+    }
+    for (int c0 = 0; c0 < x.C; c0 += 8) {
+      float u[8], d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { u[j] = 0.f; d[j] = 0.f; }
+      if (ok) load8(x.hi, x.lo, v * x.ld + c0, u);
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < n_out) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            d[j] = fmaf(g[o], sw[o * x.C + c0 + j], d[j]);
+            float p = warp_sum(g[o] * u[j]);
+            if (lane == 0) atomicAdd(&sdw[o * x.C + c0 + j], p);
+          }
+        }
+      if (ok) store8(dx.hi, dx.lo, v * dx.ld + c0, d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+}
+
+int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
+                    cudaStream_t st) {
+  B200_REQUIRE(n_out >= 1 && n_out <= 8, E_UNSUPPORTED, "head_bwd: n_outputs=%d > 8 unsupported", n_out);
+  B200_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * x.C, st));
+  int blocks = ew_blocks(x.voxels(), 256);
+  if (blocks > 592) blocks = 592;
+  k_head_bwd<<<blocks, 256, 2 * n_out * x.C * sizeof(float), st>>>(x, w, n_out, dlogits, dx, dw);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// torch Conv3d weight fp32 [Co][Ci][T] (T = k^3 taps, kd-major) ->
+//   mode 0 (fwd)   : [T][Co][Ci]               B operand of  Y = conv(X, W)
+//   mode 1 (dgrad) : [T][Ci][Co] with taps flipped   B operand of  dX = conv(dY, flip(W)^T)
+//   mode 2 (convT fwd, torch ConvTranspose3d weight [Ci][Co][T]) : [T][Co][Ci] flipped
+__global__ void k_pack_weights(const float* __restrict__ w, int Co, int Ci, int Cop, int Cip, int T, int mode,
+                               bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  // Co/Ci: real extents of the torch tensor; Cop/Cip: packed (zero padded) extents.
+  const long long total = (long long)T * Cop * Cip;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (mode == 0) {
+      const int ci = (int)(i % Cip); const int co = (int)((i / Cip) % Cop); const int t = (int)(i / ((long long)Cip * Cop));
+      if (ci < Ci && co < Co) v = w[((long long)co * Ci + ci) * T + t];
+    } else if (mode == 1) {
+      const int co = (int)(i % Cop); const int ci = (int)((i / Cop) % Cip); const int t = (int)(i / ((long long)Cip * Cop));
+      if (ci < Ci && co < Co) v = w[((long long)co * Ci + ci) * T + (T - 1 - t)];
+    } else {
+      const int ci = (int)(i % Cip); const int co = (int)((i / Cip) % Cop); const int t = (int)(i / ((long long)Cip * Cop));
+      if (ci < Ci && co < Co) v = w[((long long)ci * Co + co) * T + (T - 1 - t)];
+    }
+    bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+int launch_pack_weights(const float* w, int Co, int Ci, int Cop, int Cip, int T, int mode, bf16* hi, bf16* lo,
+                        cudaStream_t st) {
+  long long total = (long long)T * Cop * Cip;
+  k_pack_weights<<<ew_blocks(total, 256), 256, 0, st>>>(w, Co, Ci, Cop, Cip, T, mode, hi, lo);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// packed fp32 gradient [T][Ci][Co] (Co contiguous; what the wgrad kernel accumulates) -> torch layout [Co][Ci][T]
+// (mode 0) or ConvTranspose3d layout [Ci][Co][T] with flipped taps (mode 2).
+__global__ void k_unpack_wgrad(const float* __restrict__ g, int Co, int Ci, int Cop, int Cip, int T, int mode,
+                               float* __restrict__ out) {
+  // g: [T][Cip][Cop] (what the wgrad kernel accumulates); out: torch layout with the real extents.
+  const long long total = (long long)T * Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      const int t = (int)(i % T); const int ci = (int)((i / T) % Ci); const int co = (int)(i / ((long long)T * Ci));
+      out[i] = g[((long long)t * Cip + ci) * Cop + co];
+    } else {
+      const int t = (int)(i % T); const int co = (int)((i / T) % Co); const int ci = (int)(i / ((long long)T * Co));
+      out[i] = g[((long long)(T - 1 - t) * Cip + ci) * Cop + co];
+    }
+  }
+}
+
+int launch_unpack_wgrad(const float* g, int Co, int Ci, int Cop, int Cip, int T, int mode, float* out,
+                        cudaStream_t st) {
+  long long total = (long long)T * Co * Ci;
+  k_unpack_wgrad<<<ew_blocks(total, 256), 256, 0, st>>>(g, Co, Ci, Cop, Cip, T, mode, out);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ zero insertion (x2 dilation)
+// z[2d+od][2h+oh][2w+ow] = x[d][h][w], zeros elsewhere; z dims given by the view (>= 2*x dims - 1 + offset).
+__global__ void k_zero_insert(Act x, Act z, int od, int oh, int ow) {
+  const int c8n = z.C / 8;
+  const long long total = z.voxels() * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    long long v = t / c8n;
+    const int w = (int)(v % z.W); v /= z.W;
+    const int h = (int)(v % z.H); v /= z.H;
+    const int d = (int)(v % z.D);
+    const int n = (int)(v / z.D);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    const int sd = d - od, sh = h - oh, sw = w - ow;
+    if (sd >= 0 && sh >= 0 && sw >= 0 && !(sd & 1) && !(sh & 1) && !(sw & 1) && (sd >> 1) < x.D && (sh >> 1) < x.H &&
+        (sw >> 1) < x.W)
+      load8(x.hi, x.lo, ((((long long)n * x.D + (sd >> 1)) * x.H + (sh >> 1)) * x.W + (sw >> 1)) * x.ld + c8 * 8, o);
+    store8(z.hi, z.lo, (t / c8n) * z.ld + c8 * 8, o);
+  }
+}
+
+int launch_zero_insert(const Act& x, const Act& z, int od, int oh, int ow, cudaStream_t st) {
+  B200_REQUIRE(x.C == z.C && x.C % 8 == 0, E_INVALID, "zero_insert: channel mismatch");
+  long long total = z.voxels() * (z.C / 8);
+  k_zero_insert<<<ew_blocks(total, 256), 256, 0, st>>>(x, z, od, oh, ow);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ layout converters (tests / boundary)
+__global__ void k_ncdhw_to_act(const float* __restrict__ x, int C, Act out) {
+  const long long S = (long long)out.D * out.H * out.W;
+  const int c8n = out.C / 8;
+  const long long total = out.N * S * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const long long vox = t / c8n;
+    const int n = (int)(vox / S);
+    const long long s = vox % S;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { int c = c8 * 8 + j; v[j] = c < C ? x[((long long)n * C + c) * S + s] : 0.f; }
+    store8(out.hi, out.lo, vox * out.ld + c8 * 8, v);
+  }
+}
+__global__ void k_act_to_ncdhw(Act in, int C, float* __restrict__ y) {
+  const long long S = (long long)in.D * in.H * in.W;
+  const int c8n = in.C / 8;
+  const long long total = in.N * S * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const long long vox = t / c8n;
+    const int n = (int)(vox / S);
+    const long long s = vox % S;
+    float v[8];
+    load8(in.hi, in.lo, vox * in.ld + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { int c = c8 * 8 + j; if (c < C) y[((long long)n * C + c) * S + s] = v[j]; }
+  }
+}
+
+int launch_ncdhw_to_act(const float* x, int C, const Act& out, cudaStream_t st) {
+  long long total = out.voxels() * (out.C / 8);
+  k_ncdhw_to_act<<<ew_blocks(total, 256), 256, 0, st>>>(x, C, out);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+int launch_act_to_ncdhw(const Act& in, int C, float* y, cudaStream_t st) {
+  long long total = in.voxels() * (in.C / 8);
+  k_act_to_ncdhw<<<ew_blocks(total, 256), 256, 0, st>>>(in, C, y);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ SIMT direct conv (debug / cross-check only)
+// y[v][co] = sum_{t,ci} x[v*stride + t - pad][ci] * wp[t][co][ci]   with packed bf16 weights (mode-0 layout).
+__global__ void k_conv_simt(Act x, const bf16* __restrict__ whi, const bf16* __restrict__ wlo, int ksz, int stride,
+                            Act y) {
+  const long long total = y.voxels() * y.C;
+  const int pad = ksz / 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(t % y.C);
+    long long v = t / y.C;
+    const int w = (int)(v % y.W); v /= y.W;
+    const int h = (int)(v % y.H); v /= y.H;
+    const int d = (int)(v % y.D);
+    const int n = (int)(v / y.D);
+    float acc = 0.f;
+    for (int kd = 0; kd < ksz; ++kd)
+      for (int kh = 0; kh < ksz; ++kh)
+        for (int kw = 0; kw < ksz; ++kw) {
+          const int id = d * stride + kd - pad, ih = h * stride + kh - pad, iw = w * stride + kw - pad;
+          if (id < 0 || ih < 0 || iw < 0 || id >= x.D || ih >= x.H || iw >= x.W) continue;
+          const long long xo = ((((long long)n * x.D + id) * x.H + ih) * x.W + iw) * x.ld;
+          const long long wo = ((long long)((kd * ksz + kh) * ksz + kw) * y.C + co) * x.C;
+          for (int ci = 0; ci < x.C; ++ci) {
+            float xv = __bfloat162float(x.hi[xo + ci]) + (x.lo ? __bfloat162float(x.lo[xo + ci]) : 0.f);
+            float wv = __bfloat162float(whi[wo + ci]) + (wlo ? __bfloat162float(wlo[wo + ci]) : 0.f);
+            acc = fmaf(xv, wv, acc);
+          }
+        }
+    const long long yo = (t / y.C) * y.ld + co;
+    bf16 hv = __float2bfloat16_rn(acc);
+    y.hi[yo] = hv;
+    if (y.lo) y.lo[yo] = __float2bfloat16_rn(acc - __bfloat162float(hv));
+  }
+}
+
+int launch_conv_simt(const Act& x, const bf16* whi, const bf16* wlo, int ksz, int stride, const Act& y,
+                     cudaStream_t st) {
+  long long total = y.voxels() * y.C;
+  k_conv_simt<<<ew_blocks(total, 128), 128, 0, st>>>(x, whi, wlo, ksz, stride, y);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,407 @@
+// 3-D convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+//   Y[v][co] = sum_{tap, ci} A[v*stride + tap - pad][ci] * Wp[tap][co][ci]          (fp32 accumulate in TMEM)
+//
+// Replaces (forward, and data-gradient with flipped/transposed packed weights):
+//   nn.Conv3d k3 s1/s2 p1, bias-free    /root/reference/unet3d/models/pytorch/classification/resnet.py:12-17
+//   nn.Conv3d k1                        /root/reference/unet3d/models/pytorch/classification/resnet.py:20-22
+// GEMM view: M = 128 output voxels (one tw x th x td spatial box of one sample), N = BN output channels,
+// K = taps x Cin walked in chunks of KC channels.  Per K step the producer thread issues two TMA loads:
+//   A: 5-D box (KC, tw, th, td, 1) of the NDHWC activation at the tap-shifted coordinate; the zero padding of the
+//      convolution is TMA out-of-bounds fill, stride-2 convolutions use the tensor map's element strides;
+//   B: 3-D box (KC, BN, 1) of the packed weights [tap][co][ci].
+// Both land K-major with the hardware swizzle that matches KC (128B/64B/32B) and feed tcgen05.mma
+// (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one thread; a STAGES-deep mbarrier ring decouples
+// TMA from MMA, tcgen05.commit releases ring slots and finally signals the epilogue warps.
+// Epilogue (4 warps, one TMEM lane quadrant each): tcgen05.ld -> registers ->
+//   mode 0: (+ residual) (* per-(n,c) dropout scale) -> bf16 hi[/lo] store, per-channel sum / sum-of-squares
+//           for the next GroupNorm (warp butterfly -> smem -> one double atomic per channel per CTA);
+//   mode 1: GroupNorm/ReLU backward: dz = dact * 1[A x + B > 0], per-channel (sum dz, sum dz*xhat).
+// Split-precision ("parity") mode runs three passes per K step: Ah*Wh, Al*Wh, Ah*Wl.
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace b200 {
+
+struct ConvMaps {
+  CUtensorMap a[2][2];  // [source][hi/lo]
+  CUtensorMap b[2][2];
+};
+
+struct ConvArgs {
+  int N, Do, Ho, Wo, Cout;
+  int tw, th, td;
+  int tiles_w, tiles_h, tiles_d;
+  int ntaps[2], ksz[2], kchunks[2], stride[2];
+  int npass;
+  int mode;
+  bf16* out_hi; bf16* out_lo; int ldo;
+  const bf16* res_hi; const bf16* res_lo; int ldr;
+  const float* scale;
+  double* stats; int stats_ld;
+  const bf16* x_hi; const bf16* x_lo; int ldx;
+  const float4* coef; int coef_ld;
+  float slope;
+  double* bstats;
+};
+
+template <int BN, int KC>
+struct ConvCfg {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BOX_BYTES = BN * KC * 2;
+  static constexpr int B_BYTES = B_BOX_BYTES < 1024 ? 1024 : B_BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;  // barriers+slot | stats | coef
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // +1024 alignment slack
+  static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
+  static constexpr uint32_t SBO = 8 * KC * 2;
+};
+
+__device__ __forceinline__ void epi_load8(const bf16* hi, const bf16* lo, long long off, float* v) {
+  uint4 a = *reinterpret_cast<const uint4*>(hi + off);
+  v[0] = bf16_lo_to_f(a.x); v[1] = bf16_hi_to_f(a.x); v[2] = bf16_lo_to_f(a.y); v[3] = bf16_hi_to_f(a.y);
+  v[4] = bf16_lo_to_f(a.z); v[5] = bf16_hi_to_f(a.z); v[6] = bf16_lo_to_f(a.w); v[7] = bf16_hi_to_f(a.w);
+  if (lo) {
+    uint4 b = *reinterpret_cast<const uint4*>(lo + off);
+    v[0] += bf16_lo_to_f(b.x); v[1] += bf16_hi_to_f(b.x); v[2] += bf16_lo_to_f(b.y); v[3] += bf16_hi_to_f(b.y);
+    v[4] += bf16_lo_to_f(b.z); v[5] += bf16_hi_to_f(b.z); v[6] += bf16_lo_to_f(b.w); v[7] += bf16_hi_to_f(b.w);
+  }
+}
+__device__ __forceinline__ void epi_store8(bf16* hi, bf16* lo, long long off, const float* v) {
+  uint4 a;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(hi + off) = a;
+  if (lo) {
+    uint4 b;
+    b.x = pack_bf16x2(v[0] - bf16_lo_to_f(a.x), v[1] - bf16_hi_to_f(a.x));
+    b.y = pack_bf16x2(v[2] - bf16_lo_to_f(a.y), v[3] - bf16_hi_to_f(a.y));
+    b.z = pack_bf16x2(v[4] - bf16_lo_to_f(a.z), v[5] - bf16_hi_to_f(a.z));
+    b.w = pack_bf16x2(v[6] - bf16_lo_to_f(a.w), v[7] - bf16_hi_to_f(a.w));
+    *reinterpret_cast<uint4*>(lo + off) = b;
+  }
+}
+
+// Transposing butterfly: every lane holds 16 column values of its own row; on return lane l holds the sum over the
+// 32 rows of column ((l >> 1) & 15)  (lanes 2k and 2k+1 hold the same column).  16 shuffles instead of 80.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    float send = up ? v[i] : v[i + 8];
+    float keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    float send = up ? v[i] : v[i + 4];
+    float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    float send = up ? v[i] : v[i + 2];
+    float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    float send = up ? v[0] : v[1];
+    float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ ConvMaps maps, const ConvArgs p) {
+  using Cfg = ConvCfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  float* s_stats = reinterpret_cast<float*>(aux + 1024);             // [BN][2]
+  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + BN * 8);   // [BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int wt = t % p.tiles_w; t /= p.tiles_w;
+  const int ht = t % p.tiles_h; t /= p.tiles_h;
+  const int dt = t % p.tiles_d;
+  const int n = t / p.tiles_d;
+  const int w0 = wt * p.tw, h0 = ht * p.th, d0 = dt * p.td;
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0][0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tfull_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;
+    for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
+    if (p.mode == 1) {
+      for (int c = e; c < BN; c += 128)
+        s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_iters = (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      int it = 0;
+      for (int src = 0; src < 2; ++src) {
+        const int nt = p.ntaps[src];
+        if (nt == 0) continue;
+        const int ks = p.ksz[src], pad = ks >> 1, sd = p.stride[src];
+        for (int tap = 0; tap < nt; ++tap) {
+          const int kd = tap / (ks * ks), kh = (tap / ks) % ks, kw = tap % ks;
+          const int cw = w0 * sd + kw - pad, ch = h0 * sd + kh - pad, cd = d0 * sd + kd - pad;
+          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+            for (int pass = 0; pass < p.npass; ++pass) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BOX_BYTES);
+              uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+              tma_load_5d(sa, &maps.a[src][pass == 1], &full_bar[s], kc * KC, cw, ch, cd, n);
+              tma_load_3d(sa + Cfg::A_BYTES, &maps.b[src][pass == 2], &full_bar[s], kc * KC, n0, tap);
+              ++it;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    const int wl = row % p.tw, hl = (row / p.tw) % p.th, dl = row / (p.tw * p.th);
+    const int w = w0 + wl, h = h0 + hl, d = d0 + dl;
+    const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
+    const long long vox = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
+#pragma unroll 1
+    for (int j = 0; j < BN / 16; ++j) {
+      const int c0 = n0 + j * 16;
+      if (c0 >= p.Cout) break;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
+      tmem_ld_wait();
+      float v[16], q[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cc = c0 + hf * 8;
+        float* vv = v + hf * 8;
+        float* qq = q + hf * 8;
+        if (cc < p.Cout && valid) {
+          if (p.mode == 0) {
+            if (p.res_hi) {
+              float rr[8];
+              epi_load8(p.res_hi, p.res_lo, vox * p.ldr + cc, rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] += rr[i];
+            }
+            if (p.scale) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qq[i] = vv[i] * vv[i];
+          } else {
+            float xx[8];
+            epi_load8(p.x_hi, p.x_lo, vox * p.ldx + cc, xx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 k = s_coef[j * 16 + hf * 8 + i];
+              const float z = fmaf(k.x, xx[i], k.y);
+              const float dz = z > 0.f ? vv[i] : vv[i] * p.slope;
+              vv[i] = dz;
+              qq[i] = dz * (xx[i] - k.z) * k.w;
+            }
+          }
+          epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { vv[i] = 0.f; qq[i] = 0.f; }
+        }
+      }
+      if (want_stats) {
+        const float s1 = warp_colsum16(v, lane);
+        const float s2 = warp_colsum16(q, lane);
+        if ((lane & 1) == 0) {
+          const int col = j * 16 + ((lane >> 1) & 15);
+          atomicAdd(&s_stats[col * 2 + 0], s1);
+          atomicAdd(&s_stats[col * 2 + 1], s2);
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (want_stats) {
+      const int e = threadIdx.x - 64;
+      double* dst = (p.mode == 0) ? p.stats : p.bstats;
+      const int ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
+      for (int c = e; c < BN; c += 128) {
+        if (n0 + c < p.Cout) {
+          atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
+          atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+static void pick_tile(int Wo, int Ho, int Do, int& tw, int& th, int& td) {
+  tw = Wo >= 8 ? 8 : Wo >= 4 ? 4 : Wo >= 2 ? 2 : 1;
+  int rem = 128 / tw;
+  th = Ho >= 4 ? 4 : Ho >= 2 ? 2 : 1;
+  if (th > rem) th = rem;
+  td = rem / th;
+}
+
+template <int BN, int KC>
+static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, KC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_igemm_conv<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  k_igemm_conv<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, args);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int launch_igemm_conv(const ConvOp& op, cudaStream_t st) {
+  B200_REQUIRE(op.nsrc == 1 || op.nsrc == 2, E_INVALID, "igemm_conv: nsrc=%d", op.nsrc);
+  const Act& out = op.out;
+  B200_REQUIRE(out.C % 8 == 0 && out.ld % 8 == 0, E_UNSUPPORTED, "igemm_conv: Cout=%d (pitch %d) must be a multiple of 8",
+               out.C, out.ld);
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  a.N = out.N; a.Do = out.D; a.Ho = out.H; a.Wo = out.W; a.Cout = out.C;
+  pick_tile(out.W, out.H, out.D, a.tw, a.th, a.td);
+  a.tiles_w = ceil_div(out.W, a.tw); a.tiles_h = ceil_div(out.H, a.th); a.tiles_d = ceil_div(out.D, a.td);
+  int cin_max = 0;
+  bool split = false;
+  for (int s = 0; s < op.nsrc; ++s) {
+    const ConvSrc& c = op.src[s];
+    B200_REQUIRE(c.ksz == 1 || c.ksz == 3, E_UNSUPPORTED, "igemm_conv: kernel_size=%d unsupported", c.ksz);
+    B200_REQUIRE(c.stride == 1 || c.stride == 2, E_UNSUPPORTED, "igemm_conv: stride=%d unsupported", c.stride);
+    B200_REQUIRE(c.x.C % 8 == 0 && c.x.ld % 8 == 0, E_UNSUPPORTED, "igemm_conv: Cin=%d must be a multiple of 8", c.x.C);
+    B200_REQUIRE(c.x.N == out.N, E_INVALID, "igemm_conv: batch mismatch");
+    const int pad = c.ksz / 2;
+    B200_REQUIRE((c.x.D + 2 * pad - c.ksz) / c.stride + 1 == out.D && (c.x.H + 2 * pad - c.ksz) / c.stride + 1 == out.H &&
+                     (c.x.W + 2 * pad - c.ksz) / c.stride + 1 == out.W,
+                 E_INVALID, "igemm_conv: source %d dims %dx%dx%d (k%d s%d) do not produce output %dx%dx%d", s, c.x.D,
+                 c.x.H, c.x.W, c.ksz, c.stride, out.D, out.H, out.W);
+    if (c.x.C > cin_max) cin_max = c.x.C;
+    if (c.x.lo || c.w_lo) split = true;
+  }
+  if (split) {
+    for (int s = 0; s < op.nsrc; ++s)
+      B200_REQUIRE(op.src[s].x.lo && op.src[s].w_lo, E_INVALID, "igemm_conv: split mode needs lo parts on every source");
+  }
+  const int KC = cin_max > 32 ? 64 : cin_max > 16 ? 32 : 16;
+  const int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
+  const Swz swz = swz_for_bytes(KC * 2);
+  for (int s = 0; s < op.nsrc; ++s) {
+    const ConvSrc& c = op.src[s];
+    a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = c.stride;
+    a.kchunks[s] = ceil_div(c.x.C, KC);
+    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
+                          c.stride, swz));
+    B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+    if (split) {
+      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
+                            c.stride, swz));
+      B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+    }
+  }
+  a.npass = split ? 3 : 1;
+  a.mode = op.mode;
+  a.out_hi = out.hi; a.out_lo = out.lo; a.ldo = out.ld;
+  if (op.res) {
+    B200_REQUIRE(op.res->C == out.C, E_INVALID, "igemm_conv: residual channel mismatch");
+    a.res_hi = op.res->hi; a.res_lo = op.res->lo; a.ldr = op.res->ld;
+  }
+  a.scale = op.scale;
+  a.stats = op.stats; a.stats_ld = op.stats_ld;
+  if (op.mode == 1) {
+    B200_REQUIRE(op.gn_x && op.coef, E_INVALID, "igemm_conv: mode 1 needs gn_x and coef");
+    B200_REQUIRE(op.gn_x->C == out.C, E_INVALID, "igemm_conv: gn_x channel mismatch");
+    a.x_hi = op.gn_x->hi; a.x_lo = op.gn_x->lo; a.ldx = op.gn_x->ld;
+    a.coef = reinterpret_cast<const float4*>(op.coef); a.coef_ld = op.coef_ld;
+    a.slope = op.slope; a.bstats = op.bstats;
+  }
+  dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN));
+#define B200_CONV_CASE(bn, kc) \
+  if (BN == bn && KC == kc) return launch_cfg<bn, kc>(maps, a, grid, st);
+  B200_CONV_CASE(16, 16) B200_CONV_CASE(16, 32) B200_CONV_CASE(16, 64)
+  B200_CONV_CASE(32, 16) B200_CONV_CASE(32, 32) B200_CONV_CASE(32, 64)
+  B200_CONV_CASE(64, 16) B200_CONV_CASE(64, 32) B200_CONV_CASE(64, 64)
+  B200_CONV_CASE(128, 16) B200_CONV_CASE(128, 32) B200_CONV_CASE(128, 64)
+#undef B200_CONV_CASE
+  set_error("igemm_conv: no kernel for BN=%d KC=%d", BN, KC);
+  return E_UNSUPPORTED;
+}
+
+}  // namespace b200

@@ -1,0 +1,87 @@
+// Internal kernel launchers of libb200unet (host API; all asynchronous on the given stream).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- bandwidth-bound kernels (elementwise.cu)
+int launch_input_pack(const float* x, int C, const Act& out, double* stats, int stats_ld, cudaStream_t st);
+int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t st);
+int launch_gn_finalize(const double* stats, const float* gamma, const float* beta, int N, int C, int Cld, int G,
+                       long long S, float eps, float* coef, cudaStream_t st);
+int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st);
+int launch_gn_bwd_finalize(const double* bstats, const float* coef, const float* gamma, int N, int C, int Cld, int G,
+                           long long S, float* coef2, float* dgamma, float* dbeta, cudaStream_t st);
+int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1, const Act* add2,
+                  const Act& dx, const float* scale, cudaStream_t st);
+int launch_add(const Act& a, const Act& b, const Act& y, cudaStream_t st);
+int launch_upsample2x_fwd(const Act& x, const Act& y, double* stats, int stats_ld, cudaStream_t st);
+int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st);
+int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st);
+int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
+                    cudaStream_t st);
+int launch_pack_weights(const float* w, int Co, int Ci, int Cop, int Cip, int T, int mode, bf16* hi, bf16* lo,
+                        cudaStream_t st);
+int launch_unpack_wgrad(const float* g, int Co, int Ci, int Cop, int Cip, int T, int mode, float* out,
+                        cudaStream_t st);
+int launch_zero_insert(const Act& x, const Act& z, int od, int oh, int ow, cudaStream_t st);
+int launch_ncdhw_to_act(const float* x, int C, const Act& out, cudaStream_t st);
+int launch_act_to_ncdhw(const Act& in, int C, float* y, cudaStream_t st);
+int launch_conv_simt(const Act& x, const bf16* whi, const bf16* wlo, int ksz, int stride, const Act& y,
+                     cudaStream_t st);
+
+// ---- Dice criterion (dice.cu)
+// flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum
+int launch_dice_fwd(const float* logits, const uint8_t* target, int N, int C, long long S, int flags,
+                    float smooth_nr, float smooth_dr, double* sums, float* loss, cudaStream_t st);
+int launch_dice_bwd(const float* logits, const uint8_t* target, int N, int C, long long S, int flags,
+                    float smooth_nr, float smooth_dr, const double* sums, const float* grad_out, float* dlogits,
+                    cudaStream_t st);
+
+// ---- tensor-core implicit-GEMM convolution (igemm_conv.cu)
+struct ConvSrc {
+  Act x;               // A operand (NDHWC bf16, hi[/lo])
+  const bf16* w_hi;    // packed weights [T][Cop][Cip] (K = Cip contiguous)
+  const bf16* w_lo;    // nullptr in single-pass mode
+  int ksz;             // 1 or 3
+  int stride;          // 1 or 2 (spatial traversal stride on x)
+  int Cip;             // packed K extent of the weights (>= x.C, multiple of 8)
+};
+
+struct ConvOp {
+  ConvSrc src[2];
+  int nsrc;            // 1, or 2 to accumulate a second (1x1x1) source into the same output tile
+  int Cop;             // packed weight rows (>= out.C)
+  Act out;             // output view (may be a channel slice of a wider buffer)
+  const Act* res;      // optional residual added before scale
+  const float* scale;  // optional [N][out.C] per-(n,c) multiplier (Dropout3d mask)
+  double* stats;       // optional [N][stats_ld][2] per-channel (sum, sumsq) of the stored output
+  int stats_ld;
+  int mode;            // 0: out = (acc + res) * scale ; 1: GroupNorm/ReLU backward epilogue
+  const Act* gn_x;     // mode 1: raw input of the norm (same shape as out)
+  const float* coef;   // mode 1: [N][coef_ld][4] (A, B, mu, rstd)
+  int coef_ld;
+  float slope;         // mode 1: negative slope of the activation (0 = ReLU)
+  double* bstats;      // mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat)
+};
+
+int launch_igemm_conv(const ConvOp& op, cudaStream_t st);
+
+// ---- tensor-core weight gradient (wgrad.cu):  dW[t][ci][co] += sum_v dy[v][co] * a[v*stride + t - pad][ci]
+struct WgradOp {
+  Act a;       // conv input (normalised activation), NDHWC
+  Act dy;      // gradient of the conv output, NDHWC (dims = conv output dims)
+  int ksz;     // 1 or 3
+  int stride;  // 1 or 2
+  int Cip;     // pitch of the [T][Cip][Cop] fp32 accumulator rows
+  int Cop;
+  float* dw;   // fp32 [T][Cip][Cop]; accumulated with atomics, caller zero-fills
+};
+int launch_wgrad(const WgradOp& op, cudaStream_t st);
+
+// ---- descriptor-semantics probe (probe.cu)
+// tests: host array [ntests][5] = (layout_mode 0:SW128 1:none, start_off_bytes, sbo_bytes, lbo_bytes, base_offset);
+// out: device float [ntests][2][128][64]  (encoding 0: A[r][k]=r, encoding 1: A[r][k]=k; B = identity) -> D[m][n]
+int launch_umma_probe(const int* tests, int ntests, float* out, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,708 @@
+// Whole-network executor: builds, once per (architecture, input shape), the static schedule of kernels that
+// reproduces the reference UNet3D forward and its autograd backward, over a caller-provided workspace arena.
+//
+// Reference graph restated (paths relative to /root/reference):
+//   encoder      unet3d/models/pytorch/segmentation/unet.py:7-16 + classification/myronenko.py:83-107
+//   res. block   classification/myronenko.py:34-58  (GN -> ReLU -> conv) x2 + identity / 1x1x1 `sample`
+//   decoder      segmentation/unet.py:19-44 + classification/decoder.py:73-130 (1x1x1 pre-conv, trilinear x2, concat)
+//   head         autoencoder/variational.py:59-60,81-87
+// State-dict order/shapes follow SURVEY.md appendix B so reference checkpoints bind by position.
+#include <functional>
+#include <string>
+#include <vector>
+#include <cstring>
+
+#include "kernels.h"
+#include "../../include/b200unet.h"
+
+namespace b200 {
+
+struct ParamInfo {
+  std::string key;
+  int64_t shape[5];
+  int ndim;
+};
+
+struct Buf {
+  size_t off_hi, off_lo;
+  int N, D, H, W, C;
+  long long stats_off;  // offset (bytes) of [N][C][2] doubles in the stats arena, or -1
+};
+
+struct TRef {
+  int buf;
+  int c0, c;
+  bool valid() const { return buf >= 0; }
+};
+static const TRef kNone = {-1, 0, 0};
+
+struct RunCtx {
+  uint8_t* ws;
+  const float* const* params;
+  float* const* grads;
+  const float* x;
+  float* logits;
+  const float* dlogits;
+  const float* drop;
+  cudaStream_t st;
+  int launches;
+};
+
+struct ConvLayer {
+  int pw;                  // parameter index
+  int Co, Ci, Cop, Cip, ksz, stride, T;
+  size_t wf_hi, wf_lo;     // packed forward weights   [T][Cop][Cip]
+  size_t wd_hi, wd_lo;     // packed data-grad weights [T][Cip][Cop]
+  size_t dw;               // fp32 accumulator         [T][Cip][Cop]
+  bool need_dgrad;
+};
+
+struct NormLayer {
+  int pg, pb;
+  int C, Cld, G;
+  long long S;
+  size_t coef, coef2, bstats;
+};
+
+struct BlockRec {
+  TRef X, a1, y1, a2, out;
+  int n1, n2, c1, c2, cs;  // indices into norms / convs (cs = -1 when no sample conv)
+  bool first;              // first block of the network: no input gradient
+  bool scale_out;          // Dropout3d scale applied to this block's output
+  bool scale_in;           // this block's input is the dropout output (its dX must be scaled)
+};
+
+struct StageRec {  // decoder up-sampling stage
+  TRef Xin;        // raw input of the 1x1x1 pre conv (low res, in_w channels)
+  TRef P;          // pre conv output (low res, out_w)
+  TRef U;          // up-sampled slice of the concat buffer
+  TRef cat;        // full concat view
+  int cpre;
+};
+
+typedef std::function<int(RunCtx&)> OpFn;
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200unet_plan {
+  b200unet_net_desc d;
+  bool split;
+  std::vector<ParamInfo> params;
+  std::vector<Buf> bufs;
+  std::vector<ConvLayer> convs;
+  std::vector<NormLayer> norms;
+  std::vector<OpFn> fwd, bwd;
+  size_t cur = 0;
+  size_t stats_off = 0, stats_bytes = 0;  // zeroed at the start of every forward
+  size_t bz_off = 0, bz_bytes = 0;        // zeroed at the start of every backward (bstats + dw accumulators)
+  int last_launches = 0;
+  int head_param = -1;
+  size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
+  bool have_drop = false;
+  std::vector<size_t> stats_allocs;  // deferred: sizes
+  std::vector<size_t> bz_allocs;
+
+  size_t alloc(size_t bytes) {
+    size_t off = (cur + 1023) & ~size_t(1023);
+    cur = off + bytes;
+    return off;
+  }
+  int find_param(const std::string& key) const {
+    for (size_t i = 0; i < params.size(); ++i)
+      if (params[i].key == key) return (int)i;
+    return -1;
+  }
+};
+
+namespace b200 {
+
+typedef b200unet_plan Plan;
+
+static int groups_for(int c, int norm_groups) { return (c < norm_groups || c % norm_groups) ? c : norm_groups; }
+
+static void add_param(Plan& P, const std::string& key, std::initializer_list<int64_t> shp) {
+  ParamInfo pi;
+  pi.key = key;
+  pi.ndim = (int)shp.size();
+  int i = 0;
+  for (int k = 0; k < 5; ++k) pi.shape[k] = 0;
+  for (auto v : shp) pi.shape[i++] = v;
+  P.params.push_back(pi);
+}
+
+static void add_block_params(Plan& P, const std::string& pre, int cin, int cout) {
+  add_param(P, pre + ".conv1.norm1.weight", {cin});
+  add_param(P, pre + ".conv1.norm1.bias", {cin});
+  add_param(P, pre + ".conv1.conv.weight", {cout, cin, 3, 3, 3});
+  add_param(P, pre + ".conv2.norm1.weight", {cout});
+  add_param(P, pre + ".conv2.norm1.bias", {cout});
+  add_param(P, pre + ".conv2.conv.weight", {cout, cout, 3, 3, 3});
+  if (cin != cout) add_param(P, pre + ".sample.weight", {cout, cin, 1, 1, 1});
+}
+
+static void dec_widths(const b200unet_net_desc& d, int depth, int* in_w, int* out_w) {
+  int L = d.n_levels;
+  int o, i;
+  if (depth > 0) {
+    o = d.base_width;
+    for (int k = 0; k < depth - 1; ++k) o *= d.feature_dilation;
+    i = o * d.feature_dilation;
+  } else {
+    o = d.base_width;
+    i = d.base_width;
+  }
+  if (depth != L - 1) i *= 2;
+  *in_w = i;
+  *out_w = o;
+}
+
+static void build_param_spec(Plan& P) {
+  const b200unet_net_desc& d = P.d;
+  const int L = d.n_levels;
+  int cin = d.n_features;
+  int w = d.base_width;
+  std::vector<int> widths;
+  for (int li = 0; li < L; ++li) { widths.push_back(w); w *= d.feature_dilation; }
+  for (int li = 0; li < L; ++li) {
+    for (int b = 0; b < d.encoder_blocks[li]; ++b)
+      add_block_params(P, "encoder.layers." + std::to_string(li) + ".blocks." + std::to_string(b),
+                       b == 0 ? cin : widths[li], widths[li]);
+    cin = widths[li];
+  }
+  for (int li = 0; li + 1 < L; ++li)
+    add_param(P, "encoder.downsampling_convolutions." + std::to_string(li) + ".weight", {widths[li], widths[li], 3, 3, 3});
+  for (int i = 0; i < L; ++i) {
+    int depth = L - 1 - i, in_w, out_w;
+    dec_widths(d, depth, &in_w, &out_w);
+    int planes = depth != 0 ? in_w : out_w;
+    for (int b = 0; b < d.decoder_blocks[i]; ++b)
+      add_block_params(P, "decoder.layers." + std::to_string(i) + ".blocks." + std::to_string(b), b == 0 ? in_w : planes,
+                       planes);
+  }
+  for (int i = 0; i + 1 < L; ++i) {
+    int in_w, out_w;
+    dec_widths(d, L - 1 - i, &in_w, &out_w);
+    if (d.use_transposed_convolutions) {
+      add_param(P, "decoder.upsampling_blocks." + std::to_string(i) + ".weight", {in_w, out_w, 3, 3, 3});
+      add_param(P, "decoder.upsampling_blocks." + std::to_string(i) + ".bias", {out_w});
+    } else {
+      add_param(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", {out_w, in_w, 1, 1, 1});
+    }
+  }
+  add_param(P, "final_convolution.weight", {d.n_outputs, d.base_width, 1, 1, 1});
+}
+
+// ------------------------------------------------------------------------------------------------ builders
+static int new_buf(Plan& P, int N, int D, int H, int W, int C) {
+  Buf b;
+  size_t bytes = (size_t)N * D * H * W * C * sizeof(bf16);
+  b.off_hi = P.alloc(bytes);
+  b.off_lo = P.split ? P.alloc(bytes) : 0;
+  b.N = N; b.D = D; b.H = H; b.W = W; b.C = C;
+  b.stats_off = -1;
+  P.bufs.push_back(b);
+  return (int)P.bufs.size() - 1;
+}
+
+static TRef full(const Plan& P, int buf) { TRef t = {buf, 0, P.bufs[buf].C}; return t; }
+static TRef slice(TRef t, int c0, int c) { TRef r = {t.buf, t.c0 + c0, c}; return r; }
+
+static Act act_of(const Plan& P, const RunCtx& cx, TRef t) {
+  const Buf& b = P.bufs[t.buf];
+  bf16* hi = reinterpret_cast<bf16*>(cx.ws + b.off_hi) + t.c0;
+  bf16* lo = P.split ? reinterpret_cast<bf16*>(cx.ws + b.off_lo) + t.c0 : nullptr;
+  return make_act(hi, lo, b.N, b.D, b.H, b.W, t.c, b.C);
+}
+
+static void need_stats(Plan& P, int buf) {
+  Buf& b = P.bufs[buf];
+  if (b.stats_off >= 0) return;
+  b.stats_off = (long long)P.stats_bytes;
+  P.stats_bytes += ((size_t)b.N * b.C * 2 * sizeof(double) + 255) & ~size_t(255);
+}
+static double* stats_ptr(const Plan& P, const RunCtx& cx, TRef t) {
+  const Buf& b = P.bufs[t.buf];
+  return reinterpret_cast<double*>(cx.ws + P.stats_off + b.stats_off) + (size_t)t.c0 * 2;
+}
+
+static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, int stride, bool need_dgrad) {
+  ConvLayer c;
+  c.pw = P.find_param(key);
+  c.Co = Co; c.Ci = Ci; c.Cop = round_up(Co, 8); c.Cip = round_up(Ci, 8);
+  c.ksz = ksz; c.stride = stride; c.T = ksz * ksz * ksz;
+  c.need_dgrad = need_dgrad;
+  size_t n = (size_t)c.T * c.Cop * c.Cip;
+  c.wf_hi = P.alloc(n * 2);
+  c.wf_lo = P.split ? P.alloc(n * 2) : 0;
+  c.wd_hi = need_dgrad ? P.alloc(n * 2) : 0;
+  c.wd_lo = (need_dgrad && P.split) ? P.alloc(n * 2) : 0;
+  c.dw = P.bz_bytes;  // relative to bz_off
+  P.bz_bytes += (n * sizeof(float) + 255) & ~size_t(255);
+  P.convs.push_back(c);
+  return (int)P.convs.size() - 1;
+}
+
+static int new_norm(Plan& P, const std::string& prefix, int C, int Cld, long long S) {
+  NormLayer n;
+  n.pg = P.find_param(prefix + ".weight");
+  n.pb = P.find_param(prefix + ".bias");
+  n.C = C; n.Cld = Cld; n.G = groups_for(C, P.d.norm_groups); n.S = S;
+  n.coef = P.alloc((size_t)P.d.batch * Cld * 4 * sizeof(float));
+  n.coef2 = P.alloc((size_t)P.d.batch * Cld * 2 * sizeof(float));
+  n.bstats = P.bz_bytes;
+  P.bz_bytes += ((size_t)P.d.batch * Cld * 2 * sizeof(double) + 255) & ~size_t(255);
+  P.norms.push_back(n);
+  return (int)P.norms.size() - 1;
+}
+
+#define LAUNCHED(cx, expr) do { B200_TRY(expr); (cx).launches++; } while (0)
+
+// ---- forward op emitters
+static void emit_pack(Plan& P, int ci) {
+  P.fwd.push_back([&P, ci](RunCtx& cx) -> int {
+    const ConvLayer& c = P.convs[ci];
+    const float* w = cx.params[c.pw];
+    LAUNCHED(cx, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 0, reinterpret_cast<bf16*>(cx.ws + c.wf_hi),
+                                     P.split ? reinterpret_cast<bf16*>(cx.ws + c.wf_lo) : nullptr, cx.st));
+    if (c.need_dgrad)
+      LAUNCHED(cx, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 1, reinterpret_cast<bf16*>(cx.ws + c.wd_hi),
+                                       P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr, cx.st));
+    return OK;
+  });
+}
+
+static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
+  P.fwd.push_back([&P, ni, x, y](RunCtx& cx) -> int {
+    const NormLayer& n = P.norms[ni];
+    LAUNCHED(cx, launch_gn_finalize(stats_ptr(P, cx, x), cx.params[n.pg], cx.params[n.pb], P.d.batch, n.C, n.Cld, n.G,
+                                    n.S, 1e-5f, reinterpret_cast<float*>(cx.ws + n.coef), cx.st));
+    LAUNCHED(cx, launch_gn_apply(act_of(P, cx, x), act_of(P, cx, y), reinterpret_cast<float*>(cx.ws + n.coef), 0.f,
+                                 cx.st));
+    return OK;
+  });
+}
+
+// generic forward-weights conv:  out = (conv(a, W[ci]) [+ conv1x1(a2, W[ci2])] [+ res]) [* dropout]
+static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, TRef out, bool stats, bool scale) {
+  if (stats) need_stats(P, out.buf);
+  P.fwd.push_back([&P, ci, a, ci2, a2, res, out, stats, scale](RunCtx& cx) -> int {
+    const ConvLayer& c = P.convs[ci];
+    ConvOp op;
+    memset(&op, 0, sizeof(op));
+    op.nsrc = 1;
+    op.src[0].x = act_of(P, cx, a);
+    op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wf_hi);
+    op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wf_lo) : nullptr;
+    op.src[0].ksz = c.ksz; op.src[0].stride = c.stride; op.src[0].Cip = c.Cip;
+    op.Cop = c.Cop;
+    if (ci2 >= 0) {
+      const ConvLayer& c2 = P.convs[ci2];
+      op.nsrc = 2;
+      op.src[1].x = act_of(P, cx, a2);
+      op.src[1].w_hi = reinterpret_cast<bf16*>(cx.ws + c2.wf_hi);
+      op.src[1].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c2.wf_lo) : nullptr;
+      op.src[1].ksz = c2.ksz; op.src[1].stride = c2.stride; op.src[1].Cip = c2.Cip;
+    }
+    op.out = act_of(P, cx, out);
+    Act r;
+    if (res.valid()) { r = act_of(P, cx, res); op.res = &r; }
+    if (scale && cx.drop) op.scale = cx.drop;
+    if (stats) { op.stats = stats_ptr(P, cx, out); op.stats_ld = P.bufs[out.buf].C; }
+    LAUNCHED(cx, launch_igemm_conv(op, cx.st));
+    return OK;
+  });
+}
+
+// ---- backward op emitters
+static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
+  P.bwd.push_back([&P, ci, a, dy](RunCtx& cx) -> int {
+    const ConvLayer& c = P.convs[ci];
+    WgradOp op;
+    op.a = act_of(P, cx, a);
+    op.dy = act_of(P, cx, dy);
+    op.ksz = c.ksz; op.stride = c.stride; op.Cip = c.Cip; op.Cop = c.Cop;
+    op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
+    LAUNCHED(cx, launch_wgrad(op, cx.st));
+    return OK;
+  });
+}
+
+// data gradient through conv `ci` (stride 1):  out = conv(dy, Wd)  with either the GN/ReLU backward epilogue
+// (ni >= 0, gn_x = raw input of the norm) or a plain epilogue (+res, *dropout scale).
+static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale) {
+  P.bwd.push_back([&P, ci, dy, out, ni, gn_x, res, scale](RunCtx& cx) -> int {
+    const ConvLayer& c = P.convs[ci];
+    ConvOp op;
+    memset(&op, 0, sizeof(op));
+    op.nsrc = 1;
+    op.src[0].x = act_of(P, cx, dy);
+    op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wd_hi);
+    op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr;
+    op.src[0].ksz = c.ksz; op.src[0].stride = 1; op.src[0].Cip = c.Cop;  // K extent of Wd = Cop
+    op.Cop = c.Cip;                                                       // rows of Wd = Cip
+    op.out = act_of(P, cx, out);
+    Act r, gx;
+    if (res.valid()) { r = act_of(P, cx, res); op.res = &r; }
+    if (scale && cx.drop) op.scale = cx.drop;
+    if (ni >= 0) {
+      const NormLayer& n = P.norms[ni];
+      op.mode = 1;
+      gx = act_of(P, cx, gn_x);
+      op.gn_x = &gx;
+      op.coef = reinterpret_cast<float*>(cx.ws + n.coef);
+      op.coef_ld = n.Cld;
+      op.slope = 0.f;
+      op.bstats = reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats);
+    }
+    LAUNCHED(cx, launch_igemm_conv(op, cx.st));
+    return OK;
+  });
+}
+
+static void emit_gn_bwd_finalize(Plan& P, int ni) {
+  P.bwd.push_back([&P, ni](RunCtx& cx) -> int {
+    const NormLayer& n = P.norms[ni];
+    LAUNCHED(cx, launch_gn_bwd_finalize(reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats),
+                                        reinterpret_cast<float*>(cx.ws + n.coef), cx.params[n.pg], P.d.batch, n.C, n.Cld,
+                                        n.G, n.S, reinterpret_cast<float*>(cx.ws + n.coef2), cx.grads[n.pg],
+                                        cx.grads[n.pb], cx.st));
+    return OK;
+  });
+}
+
+static void emit_gn_bwd(Plan& P, int ni, TRef dz, TRef x, TRef add1, TRef dx, bool scale) {
+  P.bwd.push_back([&P, ni, dz, x, add1, dx, scale](RunCtx& cx) -> int {
+    const NormLayer& n = P.norms[ni];
+    Act a1;
+    if (add1.valid()) a1 = act_of(P, cx, add1);
+    LAUNCHED(cx, launch_gn_bwd(act_of(P, cx, dz), act_of(P, cx, x), reinterpret_cast<float*>(cx.ws + n.coef),
+                               reinterpret_cast<float*>(cx.ws + n.coef2), add1.valid() ? &a1 : nullptr, nullptr,
+                               act_of(P, cx, dx), (scale && cx.drop) ? cx.drop : nullptr, cx.st));
+    return OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ residual block
+static BlockRec build_block_fwd(Plan& P, const std::string& pre, TRef X, int cin_real, int C, TRef dest, bool want_stats,
+                                bool first, bool scale_out, bool scale_in) {
+  const Buf& xb = P.bufs[X.buf];
+  const int N = xb.N, D = xb.D, H = xb.H, W = xb.W;
+  const long long S = (long long)D * H * W;
+  BlockRec r;
+  r.X = X; r.first = first; r.scale_out = scale_out; r.scale_in = scale_in;
+  r.n1 = new_norm(P, pre + ".conv1.norm1", cin_real, X.c, S);
+  r.c1 = new_conv(P, pre + ".conv1.conv.weight", C, cin_real, 3, 1, true);
+  r.n2 = new_norm(P, pre + ".conv2.norm1", C, C, S);
+  r.c2 = new_conv(P, pre + ".conv2.conv.weight", C, C, 3, 1, true);
+  r.cs = (cin_real != C) ? new_conv(P, pre + ".sample.weight", C, cin_real, 1, 1, !first) : -1;
+  r.a1 = full(P, new_buf(P, N, D, H, W, X.c));
+  r.y1 = full(P, new_buf(P, N, D, H, W, C));
+  r.a2 = full(P, new_buf(P, N, D, H, W, C));
+  r.out = dest;
+  emit_pack(P, r.c1);
+  emit_pack(P, r.c2);
+  if (r.cs >= 0) emit_pack(P, r.cs);
+  emit_norm_fwd(P, r.n1, X, r.a1);
+  emit_conv_fwd(P, r.c1, r.a1, -1, kNone, kNone, r.y1, true, false);
+  emit_norm_fwd(P, r.n2, r.y1, r.a2);
+  if (r.cs >= 0) emit_conv_fwd(P, r.c2, r.a2, r.cs, X, kNone, dest, want_stats, scale_out);
+  else emit_conv_fwd(P, r.c2, r.a2, -1, kNone, X, dest, want_stats, scale_out);
+  return r;
+}
+
+// returns the TRef of dX (kNone for the first block of the network)
+static TRef build_block_bwd(Plan& P, const BlockRec& r, TRef dOut) {
+  const Buf& xb = P.bufs[r.X.buf];
+  const int N = xb.N, D = xb.D, H = xb.H, W = xb.W;
+  const int C = r.y1.c;
+  emit_wgrad(P, r.c2, r.a2, dOut);
+  if (r.cs >= 0) emit_wgrad(P, r.cs, r.X, dOut);
+  TRef dz2 = full(P, new_buf(P, N, D, H, W, C));
+  emit_dgrad(P, r.c2, dOut, dz2, r.n2, r.y1, kNone, false);
+  emit_gn_bwd_finalize(P, r.n2);
+  TRef dy1 = full(P, new_buf(P, N, D, H, W, C));
+  emit_gn_bwd(P, r.n2, dz2, r.y1, kNone, dy1, false);
+  emit_wgrad(P, r.c1, r.a1, dy1);
+  TRef dz1 = full(P, new_buf(P, N, D, H, W, r.X.c));
+  emit_dgrad(P, r.c1, dy1, dz1, r.n1, r.X, kNone, false);
+  emit_gn_bwd_finalize(P, r.n1);
+  if (r.first) return kNone;
+  TRef dX = full(P, new_buf(P, N, D, H, W, r.X.c));
+  if (r.cs >= 0) {
+    emit_gn_bwd(P, r.n1, dz1, r.X, kNone, dX, false);
+    emit_dgrad(P, r.cs, dOut, dX, -1, kNone, dX, r.scale_in);  // dX = (conv1x1(dOut, Ws^T) + dX) [* scale]
+  } else {
+    emit_gn_bwd(P, r.n1, dz1, r.X, dOut, dX, r.scale_in);
+  }
+  return dX;
+}
+
+static int build(Plan& P) {
+  const b200unet_net_desc& d = P.d;
+  const int L = d.n_levels, N = d.batch;
+  B200_REQUIRE(L >= 2 && L <= 8, E_UNSUPPORTED, "plan: n_levels=%d unsupported (2..8)", L);
+  B200_REQUIRE(!d.use_transposed_convolutions, E_UNSUPPORTED, "plan: use_transposed_convolutions not implemented yet");
+  B200_REQUIRE(d.base_width % 8 == 0, E_UNSUPPORTED, "plan: base_width=%d must be a multiple of 8", d.base_width);
+  B200_REQUIRE(d.n_features >= 1 && d.n_features <= 16, E_UNSUPPORTED, "plan: n_features=%d unsupported", d.n_features);
+  B200_REQUIRE(d.n_outputs >= 1 && d.n_outputs <= 8, E_UNSUPPORTED, "plan: n_outputs=%d unsupported", d.n_outputs);
+  std::vector<int> widths, Ds, Hs, Ws;
+  {
+    int w = d.base_width, D = d.depth, H = d.height, W = d.width;
+    for (int li = 0; li < L; ++li) {
+      widths.push_back(w); Ds.push_back(D); Hs.push_back(H); Ws.push_back(W);
+      if (li + 1 < L)
+        B200_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D >= 2 && H >= 2 && W >= 2, E_UNSUPPORTED,
+                     "plan: level %d extent %dx%dx%d must be even (input %dx%dx%d not divisible by 2^%d)", li, D, H, W,
+                     d.depth, d.height, d.width, L - 1);
+      w *= d.feature_dilation; D /= 2; H /= 2; W /= 2;
+    }
+  }
+  build_param_spec(P);
+
+  // ---------------- forward
+  const int Cp_in = round_up(d.n_features, 8);
+  const int b_in = new_buf(P, N, Ds[0], Hs[0], Ws[0], Cp_in);
+  need_stats(P, b_in);
+  P.fwd.push_back([&P, b_in](RunCtx& cx) -> int {
+    B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.stats_off, 0, P.stats_bytes, cx.st));
+    TRef t = full(P, b_in);
+    LAUNCHED(cx, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), stats_ptr(P, cx, t), P.bufs[b_in].C, cx.st));
+    return OK;
+  });
+
+  std::vector<std::vector<BlockRec>> enc(L), dec(L);
+  std::vector<int> cat(L, -1), down(L, -1);
+  std::vector<TRef> skip(L), down_out(L);
+  std::vector<StageRec> stages;
+  for (int li = 0; li + 1 < L; ++li) {
+    cat[li] = new_buf(P, N, Ds[li], Hs[li], Ws[li], 2 * widths[li]);
+    need_stats(P, cat[li]);
+  }
+  TRef X = full(P, b_in);
+  int cin_real = d.n_features;
+  for (int li = 0; li < L; ++li) {
+    const int C = widths[li];
+    const int nb = d.encoder_blocks[li];
+    B200_REQUIRE(nb >= 1, E_INVALID, "plan: encoder_blocks[%d]=%d", li, nb);
+    for (int b = 0; b < nb; ++b) {
+      const bool last = (b == nb - 1);
+      TRef dest;
+      bool want_stats;
+      if (last && li + 1 < L) { dest = slice(full(P, cat[li]), C, C); want_stats = true; }
+      else { dest = full(P, new_buf(P, N, Ds[li], Hs[li], Ws[li], C)); want_stats = true; }
+      const bool first = (li == 0 && b == 0);
+      enc[li].push_back(build_block_fwd(P, "encoder.layers." + std::to_string(li) + ".blocks." + std::to_string(b), X,
+                                        cin_real, C, dest, want_stats, first, /*scale_out=*/first,
+                                        /*scale_in=*/(li == 0 && b == 1)));
+      X = dest;
+      cin_real = C;
+    }
+    skip[li] = X;
+    if (li + 1 < L) {
+      down[li] = new_conv(P, "encoder.downsampling_convolutions." + std::to_string(li) + ".weight", C, C, 3, 2, true);
+      emit_pack(P, down[li]);
+      down_out[li] = full(P, new_buf(P, N, Ds[li + 1], Hs[li + 1], Ws[li + 1], C));
+      emit_conv_fwd(P, down[li], X, -1, kNone, kNone, down_out[li], true, false);
+      X = down_out[li];
+    }
+  }
+  // decoder
+  for (int i = 0; i + 1 < L; ++i) {
+    const int depth = L - 1 - i;
+    int in_w, out_w;
+    dec_widths(d, depth, &in_w, &out_w);
+    B200_REQUIRE(in_w == X.c, E_INVALID, "plan: decoder stage %d expects %d channels, has %d", i, in_w, X.c);
+    const Buf xb = P.bufs[X.buf];
+    for (int b = 0; b < d.decoder_blocks[i]; ++b) {
+      TRef dest = full(P, new_buf(P, N, xb.D, xb.H, xb.W, in_w));
+      dec[i].push_back(build_block_fwd(P, "decoder.layers." + std::to_string(i) + ".blocks." + std::to_string(b), X, in_w,
+                                       in_w, dest, /*want_stats=*/b + 1 < d.decoder_blocks[i], false, false, false));
+      X = dest;
+    }
+    const int j = L - 2 - i;
+    B200_REQUIRE(out_w == widths[j], E_INVALID, "plan: decoder stage %d width mismatch", i);
+    StageRec s;
+    s.Xin = X;
+    s.cpre = new_conv(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", out_w, in_w, 1, 1, true);
+    emit_pack(P, s.cpre);
+    s.P = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
+    emit_conv_fwd(P, s.cpre, X, -1, kNone, kNone, s.P, false, false);
+    s.cat = full(P, cat[j]);
+    s.U = slice(s.cat, 0, out_w);
+    {
+      TRef Pin = s.P, U = s.U;
+      P.fwd.push_back([&P, Pin, U](RunCtx& cx) -> int {
+        LAUNCHED(cx, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
+                                           cx.st));
+        return OK;
+      });
+    }
+    stages.push_back(s);
+    X = s.cat;
+  }
+  // final stage (depth 0)
+  {
+    const Buf xb = P.bufs[X.buf];
+    int cin = X.c;
+    for (int b = 0; b < d.decoder_blocks[L - 1]; ++b) {
+      TRef dest = full(P, new_buf(P, N, xb.D, xb.H, xb.W, d.base_width));
+      dec[L - 1].push_back(build_block_fwd(P, "decoder.layers." + std::to_string(L - 1) + ".blocks." + std::to_string(b), X,
+                                           cin, d.base_width, dest, b + 1 < d.decoder_blocks[L - 1], false, false, false));
+      X = dest;
+      cin = d.base_width;
+    }
+  }
+  const TRef Xfinal = X;
+  P.head_param = P.find_param("final_convolution.weight");
+  P.fwd.push_back([&P, Xfinal](RunCtx& cx) -> int {
+    LAUNCHED(cx, launch_head_fwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, P.d.activation, cx.logits,
+                                 cx.st));
+    return OK;
+  });
+
+  // ---------------- backward
+  B200_REQUIRE(d.activation == 0, E_UNSUPPORTED,
+               "plan: activation inside the model (sigmoid/softmax) is inference-only; train on logits");
+  P.bwd.push_back([&P](RunCtx& cx) -> int {
+    B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.bz_off, 0, P.bz_bytes, cx.st));
+    return OK;
+  });
+  TRef g;
+  {
+    const Buf xb = P.bufs[Xfinal.buf];
+    g = full(P, new_buf(P, N, xb.D, xb.H, xb.W, Xfinal.c));
+    TRef gg = g;
+    P.bwd.push_back([&P, Xfinal, gg](RunCtx& cx) -> int {
+      LAUNCHED(cx, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits,
+                                   act_of(P, cx, gg), cx.grads[P.head_param], cx.st));
+      return OK;
+    });
+  }
+  for (int b = d.decoder_blocks[L - 1] - 1; b >= 0; --b) g = build_block_bwd(P, dec[L - 1][b], g);
+  std::vector<TRef> dskip_dec(L, kNone);
+  for (int i = L - 2; i >= 0; --i) {
+    const StageRec& s = stages[i];
+    const int j = L - 2 - i;
+    const int out_w = s.U.c;
+    dskip_dec[j] = slice(g, out_w, out_w);
+    TRef dU = slice(g, 0, out_w);
+    const Buf pb = P.bufs[s.P.buf];
+    TRef dP = full(P, new_buf(P, N, pb.D, pb.H, pb.W, out_w));
+    P.bwd.push_back([&P, dU, dP](RunCtx& cx) -> int {
+      LAUNCHED(cx, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
+      return OK;
+    });
+    emit_wgrad(P, s.cpre, s.Xin, dP);
+    TRef gX = full(P, new_buf(P, N, pb.D, pb.H, pb.W, s.Xin.c));
+    emit_dgrad(P, s.cpre, dP, gX, -1, kNone, kNone, false);
+    for (int b = d.decoder_blocks[i] - 1; b >= 0; --b) gX = build_block_bwd(P, dec[i][b], gX);
+    g = gX;
+  }
+  // g = gradient w.r.t. the bottleneck output (skip[L-1])
+  for (int li = L - 1; li >= 0; --li) {
+    for (int b = d.encoder_blocks[li] - 1; b >= 0; --b) g = build_block_bwd(P, enc[li][b], g);
+    if (li > 0) {
+      const int lj = li - 1;
+      emit_wgrad(P, down[lj], skip[lj], g);
+      TRef Z = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
+      TRef gin = g;
+      P.bwd.push_back([&P, gin, Z](RunCtx& cx) -> int {
+        LAUNCHED(cx, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
+        return OK;
+      });
+      TRef gS = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
+      // dropout scale belongs to the output of encoder block (0,0): that is this tensor iff level 0 has one block
+      const bool sc = (lj == 0 && d.encoder_blocks[0] == 1);
+      emit_dgrad(P, down[lj], Z, gS, -1, kNone, dskip_dec[lj], sc);
+      g = gS;
+    }
+  }
+  // weight gradients: accumulator -> torch layout
+  for (size_t ci = 0; ci < P.convs.size(); ++ci) {
+    P.bwd.push_back([&P, ci](RunCtx& cx) -> int {
+      const ConvLayer& c = P.convs[ci];
+      LAUNCHED(cx, launch_unpack_wgrad(reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw), c.Co, c.Ci, c.Cop, c.Cip, c.T, 0,
+                                       cx.grads[c.pw], cx.st));
+      return OK;
+    });
+  }
+  // arenas that are bulk-zeroed
+  P.drop_off = P.alloc(sizeof(float) * N * d.base_width);
+  P.stats_off = P.alloc(P.stats_bytes);
+  P.bz_off = P.alloc(P.bz_bytes);
+  for (size_t i = 0; i < P.convs.size(); ++i)
+    B200_REQUIRE(P.convs[i].pw >= 0, E_INVALID, "plan: internal: conv %d has no parameter", (int)i);
+  return OK;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200unet_plan_create(const b200unet_net_desc* desc, b200unet_plan** out) {
+  if (!desc || !out) { set_error("plan_create: null argument"); return E_INVALID; }
+  b200unet_plan* P = new b200unet_plan();
+  P->d = *desc;
+  P->split = desc->split_precision != 0;
+  if (P->d.norm_groups <= 0) P->d.norm_groups = 8;
+  if (P->d.feature_dilation <= 0) P->d.feature_dilation = 2;
+  int s = build(*P);
+  if (s != OK) { delete P; *out = nullptr; return s; }
+  *out = P;
+  return OK;
+}
+
+void b200unet_plan_destroy(b200unet_plan* plan) { delete plan; }
+
+int b200unet_plan_num_params(const b200unet_plan* plan) { return plan ? (int)plan->params.size() : 0; }
+
+int b200unet_plan_param_info(const b200unet_plan* plan, int i, int64_t shape[5], char* key, int key_cap) {
+  if (!plan || i < 0 || i >= (int)plan->params.size()) { set_error("param_info: index out of range"); return E_INVALID; }
+  const ParamInfo& p = plan->params[i];
+  for (int k = 0; k < 5; ++k) shape[k] = p.shape[k];
+  if (key && key_cap > 0) { strncpy(key, p.key.c_str(), key_cap - 1); key[key_cap - 1] = 0; }
+  return p.ndim;
+}
+
+size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan) { return plan ? plan->cur + 1024 : 0; }
+
+int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
+                          int save_for_backward, void* workspace, float* logits, void* stream) {
+  (void)save_for_backward;
+  if (!plan || !x || !params || !workspace || !logits) { set_error("plan_forward: null argument"); return E_INVALID; }
+  RunCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  cx.ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  cx.params = params; cx.x = x; cx.logits = logits;
+  cx.st = reinterpret_cast<cudaStream_t>(stream);
+  plan->have_drop = dropout_scale != nullptr;
+  if (dropout_scale) {
+    float* dst = reinterpret_cast<float*>(cx.ws + plan->drop_off);
+    if (cudaMemcpyAsync(dst, dropout_scale, sizeof(float) * plan->d.batch * plan->d.base_width, cudaMemcpyDeviceToDevice,
+                        cx.st) != cudaSuccess) { set_error("plan_forward: dropout copy failed"); return E_CUDA; }
+    cx.drop = dst;
+  }
+  for (auto& op : plan->fwd) { int s = op(cx); if (s != OK) return s; }
+  plan->last_launches = cx.launches;
+  return OK;
+}
+
+int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const float* const* params, float* const* grads,
+                           void* workspace, void* stream) {
+  if (!plan || !dlogits || !params || !grads || !workspace) { set_error("plan_backward: null argument"); return E_INVALID; }
+  RunCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  cx.ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  cx.params = params; cx.grads = grads; cx.dlogits = dlogits;
+  cx.st = reinterpret_cast<cudaStream_t>(stream);
+  if (plan->have_drop) cx.drop = reinterpret_cast<float*>(cx.ws + plan->drop_off);
+  for (auto& op : plan->bwd) { int s = op(cx); if (s != OK) return s; }
+  plan->last_launches = cx.launches;
+  return OK;
+}
+
+int b200unet_plan_last_launches(const b200unet_plan* plan) { return plan ? plan->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,20 @@
+// Host-side TMA tensor-map construction (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint,
+// so the library has no link-time dependency on libcuda).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum Swz { SWZ_NONE = 0, SWZ_32 = 1, SWZ_64 = 2, SWZ_128 = 3 };
+
+// 5-D map over an NDHWC bf16 view: dims (C, W, H, D, N).  box = (boxC, boxW, boxH, boxD, 1) elements *loaded*;
+// estride = traversal stride on the three spatial dims (1, or 2 for the stride-2 convolutions).
+int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int boxC, int boxW,
+                 int boxH, int boxD, int estride, Swz swz);
+
+// 3-D map over packed weights [T][R][K] bf16 (K contiguous): dims (K, R, T); box (boxK, boxR, 1).
+int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz);
+
+static inline Swz swz_for_bytes(int bytes) { return bytes >= 128 ? SWZ_128 : bytes >= 64 ? SWZ_64 : SWZ_32; }
+
+}  // namespace b200

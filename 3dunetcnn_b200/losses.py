@@ -1,0 +1,64 @@
+"""Fused Dice criterion -- the class ``load_criterion`` finds first.
+
+The reference resolves ``config["loss"]["name"]`` in ``unet3d.losses`` before ``torch.nn`` and ``monai.losses``
+(/root/reference/unet3d/scripts/script_utils.py:64-73; the shipped module is an empty hook,
+unet3d/losses/losses.py:1-3), so a class named ``DiceLoss`` placed here takes over
+``{"name": "DiceLoss", "include_background": true, "sigmoid": true}``
+(examples/brats2020/brats2020_config.json:112-116) with MONAI's kwarg names.  Forward and backward are the
+hand-written kernels ``b200unet_dice_fwd`` / ``b200unet_dice_bwd``; targets stay uint8 in HBM.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+
+
+class _DiceFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, flags, nr, dr):
+        n, c = logits.shape[:2]
+        sums = torch.empty((n, c, 3), dtype=torch.float64, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        _lib.dice_fwd(logits, target, flags, nr, dr, sums, loss)
+        ctx.save_for_backward(logits, target, sums)
+        ctx.cfg = (flags, nr, dr)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, target, sums = ctx.saved_tensors
+        flags, nr, dr = ctx.cfg
+        dlogits = torch.empty_like(logits)
+        g = grad_out.detach().float().contiguous()
+        _lib.dice_bwd(logits, target, flags, nr, dr, sums, g, dlogits)
+        return dlogits, None, None, None, None
+
+
+class DiceLoss(nn.Module):
+    """MONAI-compatible signature; only the options the kernels implement are accepted (others raise)."""
+
+    def __init__(self, include_background=True, to_onehot_y=False, sigmoid=False, softmax=False, other_act=None,
+                 squared_pred=False, jaccard=False, reduction="mean", smooth_nr=1e-5, smooth_dr=1e-5, batch=False,
+                 weight=None, **unused):
+        super().__init__()
+        if softmax or to_onehot_y or other_act is not None or weight is not None:
+            raise NotImplementedError("fused DiceLoss: softmax / to_onehot_y / other_act / weight are not implemented")
+        if reduction not in ("mean", "sum"):
+            raise NotImplementedError("fused DiceLoss: reduction=%r (only 'mean'/'sum')" % (reduction,))
+        self.flags = _lib.dice_flags(sigmoid=sigmoid, squared_pred=squared_pred, jaccard=jaccard, batch=batch,
+                                     include_background=include_background, reduction=reduction)
+        self.smooth_nr, self.smooth_dr = float(smooth_nr), float(smooth_dr)
+
+    def forward(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if not output.is_cuda:
+            raise RuntimeError("fused DiceLoss runs only on CUDA tensors (no CPU fallback)")
+        if output.shape != target.shape:
+            raise AssertionError("ground truth has different shape (%s) from input (%s)" % (tuple(target.shape), tuple(output.shape)))
+        out = output.as_subclass(torch.Tensor) if type(output) is not torch.Tensor else output
+        tgt = target.as_subclass(torch.Tensor) if type(target) is not torch.Tensor else target
+        out = out.contiguous().float()
+        if tgt.dtype != torch.uint8:
+            tgt = tgt.to(torch.uint8)
+        return _DiceFunction.apply(out, tgt.contiguous(), self.flags, self.smooth_nr, self.smooth_dr)

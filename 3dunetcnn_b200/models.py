@@ -1,0 +1,381 @@
+"""Host-side mirror of the reference's model interface for the U-Net path.
+
+Mirrors (paths relative to /root/reference):
+  * ``unet3d/models/pytorch/segmentation/unet.py:47-70``  UNet3D / AutocastUNet / AutoImplantUNet
+  * ``unet3d/models/pytorch/autoencoder/variational.py:37-87`` ctor kwargs + forward contract
+  * ``unet3d/models/build.py:9-64``  fetch_model_by_name / build_or_load_model / load_state_dict
+
+The module keeps canonical fp32 parameters under the reference's state-dict keys (so reference checkpoints load and
+checkpoints written here load into the reference), and runs forward/backward as ONE call each into libb200unet's
+whole-network plan (hand-written sm_100a kernels).  There is no PyTorch-op fallback: on a non-CUDA tensor, or if
+the library is missing, ``forward`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+
+_ACT = {None: 0, "sigmoid": 1, "softmax": 2}
+
+
+class _Node(nn.Module):
+    """Plain container used to reproduce the reference's dotted state-dict keys."""
+
+
+def _register(root: nn.Module, key: str, param: nn.Parameter) -> None:
+    parts = key.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], param)
+
+
+class _Plan:
+    """Owns one ``b200unet_plan`` + its workspace for a fixed (batch, D, H, W, precision, device)."""
+
+    def __init__(self, desc: _lib.NetDesc, device: torch.device):
+        self.lib = _lib.load_library()
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.b200unet_plan_create(C.byref(desc), C.byref(self.handle)), "plan_create")
+        self.n_params = self.lib.b200unet_plan_num_params(self.handle)
+        self.ws_bytes = int(self.lib.b200unet_plan_workspace_bytes(self.handle))
+        self.device = device
+        self.workspace = None
+
+    def ensure_workspace(self):
+        if self.workspace is None:
+            self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def param_spec(self):
+        out = []
+        shape = (C.c_int64 * 5)()
+        buf = C.create_string_buffer(256)
+        for i in range(self.n_params):
+            nd = self.lib.b200unet_plan_param_info(self.handle, i, shape, buf, 256)
+            out.append((buf.value.decode(), tuple(int(shape[k]) for k in range(nd))))
+        return out
+
+    def last_launches(self) -> int:
+        return int(self.lib.b200unet_plan_last_launches(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.b200unet_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _UNetFunction(torch.autograd.Function):
+    """forward+backward of the whole network as two library calls."""
+
+    @staticmethod
+    def forward(ctx, model, x, drop, *params):
+        plan = model._plan_for(x)
+        n, _, d, h, w = x.shape
+        logits = torch.empty((n, model.n_outputs, d, h, w), dtype=torch.float32, device=x.device)
+        ws = plan.ensure_workspace()
+        pa = _ptr_array(params)
+        need_bwd = any(p.requires_grad for p in params)
+        _lib.check(plan.lib.b200unet_plan_forward(plan.handle, x.data_ptr(), pa, drop.data_ptr() if drop is not None else None,
+                                                  int(need_bwd), ws.data_ptr(), logits.data_ptr(), _lib.stream_ptr()),
+                   "plan_forward")
+        model.launches_last_forward = plan.last_launches()
+        ctx.plan = plan
+        ctx.model = model
+        ctx.save_for_backward(*params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan = ctx.plan
+        params = ctx.saved_tensors
+        dlogits = dlogits.contiguous().float()
+        grads = [torch.empty_like(p) for p in params]
+        _lib.check(plan.lib.b200unet_plan_backward(plan.handle, dlogits.data_ptr(), _ptr_array(params), _ptr_array(grads),
+                                                   plan.workspace.data_ptr(), _lib.stream_ptr()), "plan_backward")
+        ctx.model.launches_last_backward = plan.last_launches()
+        return (None, None, None) + tuple(grads)
+
+
+class UNet3D(nn.Module):
+    """Drop-in for the reference ``UNet3D`` (same ctor kwargs, same state_dict), B200-native arithmetic.
+
+    Extra kwarg ``precision``: ``"bf16"`` (default; single-pass bf16 tensor-core operands, fp32 accumulate) or
+    ``"split"`` (hi/lo bf16 operand split, three MMAs per product: the parity mode that meets 1e-3 vs fp32).
+    ``B200UNET_PRECISION`` overrides the default.
+    """
+
+    def __init__(self, input_shape=None, n_features=1, base_width=32, encoder_blocks=None, decoder_blocks=None,
+                 feature_dilation=2, downsampling_stride=2, interpolation_mode="trilinear", encoder_class=None,
+                 decoder_class=None, n_outputs=1, layer_widths=None, decoder_mirrors_encoder=False, activation=None,
+                 use_transposed_convolutions=False, kernel_size=3, precision: Optional[str] = None,
+                 dropout: float = 0.2, norm_groups: int = 8):
+        super().__init__()
+        if downsampling_stride != 2:
+            raise NotImplementedError("B200 UNet3D: downsampling_stride=%r (only 2 is implemented)" % (downsampling_stride,))
+        if interpolation_mode != "trilinear":
+            raise NotImplementedError("B200 UNet3D: interpolation_mode=%r (only 'trilinear')" % (interpolation_mode,))
+        if kernel_size != 3:
+            raise NotImplementedError("B200 UNet3D: kernel_size=%r (only 3)" % (kernel_size,))
+        if layer_widths is not None:
+            raise NotImplementedError("B200 UNet3D: layer_widths is not supported (the reference's UNet3D also breaks on it)")
+        if encoder_class is not None or decoder_class is not None:
+            raise NotImplementedError("B200 UNet3D: custom encoder/decoder classes are not supported")
+        if activation not in _ACT:
+            raise ValueError("activation must be None, 'sigmoid' or 'softmax'")
+        if encoder_blocks is None:
+            encoder_blocks = [1, 2, 2, 4]                       # variational.py:44-45
+        if decoder_mirrors_encoder:
+            decoder_blocks = list(encoder_blocks)               # variational.py:71-74
+        elif decoder_blocks is None:
+            decoder_blocks = [1] * len(encoder_blocks)          # variational.py:75-76
+        if len(decoder_blocks) != len(encoder_blocks):
+            raise ValueError("decoder_blocks and encoder_blocks must have the same length")
+        precision = precision or os.environ.get("B200UNET_PRECISION", "bf16")
+        if precision not in ("bf16", "split"):
+            raise ValueError("precision must be 'bf16' or 'split'")
+        self.precision = precision
+        self.input_shape = input_shape
+        self.n_features, self.n_outputs, self.base_width = int(n_features), int(n_outputs), int(base_width)
+        self.encoder_blocks, self.decoder_blocks = [int(b) for b in encoder_blocks], [int(b) for b in decoder_blocks]
+        self.feature_dilation = int(feature_dilation)
+        self.use_transposed_convolutions = bool(use_transposed_convolutions)
+        self.activation_name = activation
+        self.dropout_p = float(dropout)                          # myronenko.py:85 (hard-wired 0.2 in the reference)
+        self.norm_groups = int(norm_groups)
+        self._plans: Dict[Tuple, _Plan] = {}
+        self.launches_last_forward = 0
+        self.launches_last_backward = 0
+        self._forced_dropout_scale: Optional[torch.Tensor] = None
+
+        # parameters under the reference's keys, default torch init
+        self._keys = []
+        spec = self._param_spec_cpu()
+        shapes = dict(spec)
+        for key, shape in spec:
+            t = torch.empty(shape, dtype=torch.float32)
+            if key.endswith("norm1.weight"):
+                nn.init.ones_(t)
+            elif key.endswith("norm1.bias"):
+                nn.init.zeros_(t)
+            else:
+                wshape = shapes[key[:-5] + ".weight"] if key.endswith(".bias") else shape
+                fan_in = wshape[1] * wshape[2] * wshape[3] * wshape[4]   # torch default: weight.size(1) * k^3
+                bound = 1.0 / math.sqrt(fan_in)
+                nn.init.uniform_(t, -bound, bound)
+            _register(self, key, nn.Parameter(t))
+            self._keys.append(key)
+
+    # ------------------------------------------------------------------ spec (pure python twin of plan.cu's)
+    def _dec_widths(self, depth: int) -> Tuple[int, int]:
+        n = len(self.encoder_blocks)
+        if depth > 0:
+            out_w = self.base_width * self.feature_dilation ** (depth - 1)
+            in_w = out_w * self.feature_dilation
+        else:
+            out_w = in_w = self.base_width
+        if depth != n - 1:
+            in_w *= 2
+        return in_w, out_w
+
+    def _param_spec_cpu(self):
+        spec = []
+
+        def block(prefix, cin, cout):
+            spec.append((prefix + ".conv1.norm1.weight", (cin,)))
+            spec.append((prefix + ".conv1.norm1.bias", (cin,)))
+            spec.append((prefix + ".conv1.conv.weight", (cout, cin, 3, 3, 3)))
+            spec.append((prefix + ".conv2.norm1.weight", (cout,)))
+            spec.append((prefix + ".conv2.norm1.bias", (cout,)))
+            spec.append((prefix + ".conv2.conv.weight", (cout, cout, 3, 3, 3)))
+            if cin != cout:
+                spec.append((prefix + ".sample.weight", (cout, cin, 1, 1, 1)))
+
+        n = len(self.encoder_blocks)
+        widths = [self.base_width * self.feature_dilation ** i for i in range(n)]
+        cin = self.n_features
+        for li, nb in enumerate(self.encoder_blocks):
+            for b in range(nb):
+                block("encoder.layers.%d.blocks.%d" % (li, b), cin if b == 0 else widths[li], widths[li])
+            cin = widths[li]
+        for li in range(n - 1):
+            spec.append(("encoder.downsampling_convolutions.%d.weight" % li, (widths[li], widths[li], 3, 3, 3)))
+        for i, nb in enumerate(self.decoder_blocks):
+            depth = n - 1 - i
+            in_w, out_w = self._dec_widths(depth)
+            planes = in_w if depth != 0 else out_w
+            for b in range(nb):
+                block("decoder.layers.%d.blocks.%d" % (i, b), in_w if b == 0 else planes, planes)
+        for i in range(n - 1):
+            in_w, out_w = self._dec_widths(n - 1 - i)
+            if self.use_transposed_convolutions:
+                spec.append(("decoder.upsampling_blocks.%d.weight" % i, (in_w, out_w, 3, 3, 3)))
+                spec.append(("decoder.upsampling_blocks.%d.bias" % i, (out_w,)))
+            else:
+                spec.append(("decoder.pre_upsampling_blocks.%d.weight" % i, (out_w, in_w, 1, 1, 1)))
+        spec.append(("final_convolution.weight", (self.n_outputs, self.base_width, 1, 1, 1)))
+        return spec
+
+    def ordered_parameters(self):
+        sd = dict(self.named_parameters())
+        return [sd[k] for k in self._keys]
+
+    # ------------------------------------------------------------------ plan cache
+    def _net_desc(self, n, d, h, w) -> _lib.NetDesc:
+        nd = _lib.NetDesc()
+        nd.n_features, nd.n_outputs, nd.base_width = self.n_features, self.n_outputs, self.base_width
+        nd.n_levels = len(self.encoder_blocks)
+        for i, b in enumerate(self.encoder_blocks):
+            nd.encoder_blocks[i] = b
+        for i, b in enumerate(self.decoder_blocks):
+            nd.decoder_blocks[i] = b
+        nd.feature_dilation = self.feature_dilation
+        nd.norm_groups = self.norm_groups
+        nd.use_transposed_convolutions = int(self.use_transposed_convolutions)
+        nd.activation = _ACT[self.activation_name]
+        nd.split_precision = int(self.precision == "split")
+        nd.batch, nd.depth, nd.height, nd.width = n, d, h, w
+        return nd
+
+    def _plan_for(self, x: torch.Tensor) -> _Plan:
+        n, _, d, h, w = x.shape
+        key = (n, d, h, w, self.precision, x.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = _Plan(self._net_desc(n, d, h, w), x.device)
+            spec = plan.param_spec()
+            mine = [(k, tuple(p.shape)) for k, p in zip(self._keys, self.ordered_parameters())]
+            if spec != mine:
+                raise RuntimeError("libb200unet parameter spec does not match the module's state_dict")
+            self._plans[key] = plan
+        return plan
+
+    def set_dropout_scale(self, scale: Optional[torch.Tensor]) -> None:
+        """Testing hook: force the (N, C0) Dropout3d channel scale used by the next training forwards."""
+        self._forced_dropout_scale = scale
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor) or x.dim() != 5:
+            raise ValueError("UNet3D expects a 5-D tensor [N, C, D, H, W]")
+        if not x.is_cuda:
+            raise RuntimeError("B200 UNet3D runs only on CUDA tensors (no CPU fallback); got device %s" % x.device)
+        if x.shape[1] != self.n_features:
+            raise ValueError("expected %d input channels, got %d" % (self.n_features, x.shape[1]))
+        if x.requires_grad:
+            raise NotImplementedError("B200 UNet3D does not produce input gradients")
+        xp = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x   # MetaTensor -> plain view
+        xp = xp.detach().contiguous().float()
+        params = self.ordered_parameters()
+        if params[0].device != xp.device:
+            raise RuntimeError("model parameters are on %s but the input is on %s" % (params[0].device, xp.device))
+        drop = None
+        if self.training and self.dropout_p > 0:
+            if self._forced_dropout_scale is not None:
+                drop = self._forced_dropout_scale.to(device=xp.device, dtype=torch.float32).contiguous()
+            else:
+                keep = (torch.rand((xp.shape[0], self.base_width), device=xp.device) >= self.dropout_p)
+                drop = keep.float() / (1.0 - self.dropout_p)
+        return _UNetFunction.apply(self, xp, drop, *params)
+
+
+class AutocastUNet(UNet3D):
+    """Reference: fp16 autocast wrapper (unet.py:53-58).  Here: the single-pass bf16 tensor-core mode."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("precision", "bf16")
+        super().__init__(*args, **kwargs)
+
+
+class AutoImplantUNet(UNet3D):
+    """unet.py:61-70: forward returns ``y - x``; ``test`` returns the plain network output."""
+
+    def forward(self, x):
+        y = super().forward(x)
+        return y - x
+
+    def test(self, x):
+        return super().forward(x)
+
+
+_MODELS = {"UNet3D": UNet3D, "AutocastUNet": AutocastUNet, "AutoImplantUNet": AutoImplantUNet,
+           "B200UNet3D": UNet3D}
+
+
+def fetch_model_by_name(model_name, *args, **kwargs):
+    """build.py:9-13."""
+    try:
+        cls = _MODELS[model_name]
+    except KeyError:
+        raise ValueError("model name {} not supported".format(model_name))
+    return cls(*args, **kwargs)
+
+
+def match_tensor_sizes(fixed_tensor, moving_tensor):
+    """build.py:54-64: tile then narrow every mismatching dim."""
+    fixed_size = fixed_tensor.size()
+    for dim in range(len(moving_tensor.size())):
+        if fixed_size[dim] > moving_tensor.size()[dim]:
+            reps = int(math.ceil(fixed_size[dim] / moving_tensor.size()[dim]))
+            moving_tensor = torch.cat([moving_tensor] * reps, dim=dim)
+        if fixed_size[dim] != moving_tensor.size()[dim]:
+            moving_tensor = moving_tensor.narrow(dim=dim, start=0, length=fixed_size[dim])
+    return moving_tensor
+
+
+def match_state_dict_shapes(fixed_state_dict, moving_state_dict):
+    """build.py:47-51."""
+    for key in fixed_state_dict:
+        if key in moving_state_dict and fixed_state_dict[key].size() != moving_state_dict[key].size():
+            moving_state_dict[key] = match_tensor_sizes(fixed_state_dict[key], moving_state_dict[key])
+    return moving_state_dict
+
+
+def load_state_dict(model, state_dict, n_gpus, strict=False):
+    """build.py:32-44 (the DataParallel retry branch is kept for wrapped models)."""
+    try:
+        if not strict:
+            state_dict = match_state_dict_shapes(model.state_dict(), state_dict)
+        model.load_state_dict(state_dict, strict=strict)
+    except RuntimeError as error:
+        if n_gpus > 1 and hasattr(model, "module"):
+            if not strict:
+                state_dict = match_state_dict_shapes(model.module.state_dict(), state_dict)
+            model.module.load_state_dict(state_dict, strict=strict)
+        else:
+            raise error
+    return model
+
+
+def build_or_load_model(model_name, model_filename, n_gpus=0, strict=False, **kwargs):
+    """build.py:16-29.  ``n_gpus > 1`` in ONE process is the reference's DataParallel branch; the B200 path is one
+    process per GPU (see ``parallel.py``), so here every n_gpus >= 1 places the replica on the current device."""
+    model = fetch_model_by_name(model_name, **kwargs)
+    if n_gpus > 0:
+        model = model.cuda()
+    if model_filename and os.path.exists(model_filename):
+        if n_gpus > 0:
+            state_dict = torch.load(model_filename)
+        else:
+            state_dict = torch.load(model_filename, map_location=torch.device("cpu"))
+        model = load_state_dict(model, state_dict, n_gpus=n_gpus, strict=strict)
+    return model

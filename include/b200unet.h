@@ -1,0 +1,162 @@
+/* libb200unet -- C ABI of the B200-native 3D U-Net forward/backward hot path.
+ *
+ * The reference (ellisdg/3DUnetCNN) has no FFI: its extension seam is the Python name lookup
+ * unet3d/models/build.py:9-13 (fetch_model_by_name) and unet3d/scripts/script_utils.py:61-77 (load_criterion).
+ * This header is the boundary a maintainer binds (ctypes stub: INTEGRATION.md); each entry point names the
+ * reference arithmetic it replaces.  All paths below are relative to the reference repository root.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library never frees or keeps
+ *     caller memory beyond a call, except the opaque plan object created/destroyed explicitly;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call synchronises the device;
+ *   - return value: 0 = ok, <0 = error (b200unet_last_error() gives a thread-local message); there is NO CPU fallback;
+ *   - activations are NDHWC bf16 "views": value = hi (+ lo when lo != NULL, the split-precision parity mode),
+ *     `c` visible channels out of a buffer with channel pitch `ld` (both multiples of 8);
+ *   - model inputs/outputs at the reference-facing boundary are NCDHW fp32, targets uint8 (as the reference's
+ *     loaders produce them: unet3d/datasets/segmentation.py:97-122, unet3d/transforms/one_hot.py:10).
+ */
+#ifndef B200UNET_H_
+#define B200UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200UNET_OK 0
+#define B200UNET_E_INVALID (-1)
+#define B200UNET_E_UNSUPPORTED (-2)
+#define B200UNET_E_CUDA (-3)
+#define B200UNET_E_DRIVER (-4)
+
+typedef struct b200unet_tensor {
+  void* hi;           /* bf16 NDHWC data */
+  void* lo;           /* bf16 residual part (value = hi + lo) or NULL */
+  int32_t n, d, h, w; /* logical extents */
+  int32_t c;          /* visible channels */
+  int32_t ld;         /* channel pitch of the underlying buffer, in elements */
+} b200unet_tensor;
+
+int b200unet_version(void);
+const char* b200unet_last_error(void);
+
+/* ---- layout converters at the NCDHW fp32 boundary (model input: unet3d/train/training_utils.py:109) */
+int b200unet_ncdhw_to_ndhwc(const float* x, int c_real, const b200unet_tensor* out, void* stream);
+int b200unet_ndhwc_to_ncdhw(const b200unet_tensor* in, int c_real, float* y, void* stream);
+
+/* ---- weight packing.  torch Conv3d weight [Co][Ci][k^3] fp32 (resnet.py:12-22) -> bf16 GEMM operand.
+ *   mode 0: [T][Cop][Cip]  forward;  mode 1: [T][Cip][Cop] taps flipped (data gradient);
+ *   mode 2: ConvTranspose3d weight [Ci][Co][k^3] (decoder.py:101-102) -> [T][Cop][Cip] flipped. */
+int b200unet_pack_weights(const float* w, int co, int ci, int cop, int cip, int taps, int mode, void* hi, void* lo,
+                          void* stream);
+/* fp32 [T][Cip][Cop] accumulator -> torch gradient layout (mode 0: [Co][Ci][T]; mode 2: [Ci][Co][T] flipped) */
+int b200unet_unpack_wgrad(const float* g, int co, int ci, int cop, int cip, int taps, int mode, float* out,
+                          void* stream);
+
+/* ---- convolution forward / data gradient: nn.Conv3d k{1,3} s{1,2} p=k/2, bias-free (resnet.py:12-22),
+ * autograd's bwd-data when called with mode-1 packed weights.  Implicit GEMM on tcgen05 tensor cores. */
+typedef struct b200unet_conv_desc {
+  b200unet_tensor x[2];    /* A operands; x[1] only when nsrc == 2 (fused 1x1x1 `sample`, myronenko.py:42-45,53-54) */
+  const void* w_hi[2];     /* packed weights per source */
+  const void* w_lo[2];
+  int32_t ksz[2];          /* 1 or 3 */
+  int32_t stride[2];       /* 1 or 2 */
+  int32_t cip[2];          /* packed K extent */
+  int32_t nsrc;
+  int32_t cop;             /* packed weight rows */
+  b200unet_tensor out;
+  const b200unet_tensor* res;   /* optional residual: `x += identity` (myronenko.py:56) */
+  const float* scale;           /* optional [N][C] Dropout3d channel scale (myronenko.py:78-79) */
+  double* stats;                /* optional [N][stats_ld][2] (sum, sumsq) for the next GroupNorm */
+  int32_t stats_ld;
+  int32_t mode;                 /* 0 plain epilogue; 1 GroupNorm+ReLU backward epilogue */
+  const b200unet_tensor* gn_x;  /* mode 1: raw input of the norm */
+  const float* coef;            /* mode 1: [N][coef_ld][4] from b200unet_gn_finalize */
+  int32_t coef_ld;
+  float slope;                  /* 0 = ReLU (myronenko.py:14), 0.01 = LeakyReLU (DynUNet blocks) */
+  double* bstats;               /* mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat) */
+} b200unet_conv_desc;
+int b200unet_conv3d(const b200unet_conv_desc* desc, void* stream);
+
+/* ---- convolution weight gradient (autograd bwd-filter of the same nn.Conv3d): dw fp32 [T][Cip][Cop] += ... */
+int b200unet_conv3d_wgrad(const b200unet_tensor* a, const b200unet_tensor* dy, int ksz, int stride, int cip, int cop,
+                          float* dw, void* stream);
+
+/* ---- SIMT direct convolution on the same packed operands (cross-check only; not used by the model path) */
+int b200unet_conv3d_simt(const b200unet_tensor* x, const void* w_hi, const void* w_lo, int ksz, int stride,
+                         const b200unet_tensor* y, void* stream);
+
+/* ---- GroupNorm(G, C, eps, affine) + ReLU (myronenko.py:17-31): statistics, apply, backward */
+int b200unet_channel_stats(const b200unet_tensor* x, double* stats, int stats_ld, void* stream);
+int b200unet_gn_finalize(const double* stats, const float* gamma, const float* beta, int n, int c, int c_ld, int groups,
+                         int64_t spatial, float eps, float* coef, void* stream);
+int b200unet_gn_apply(const b200unet_tensor* x, const b200unet_tensor* y, const float* coef, float slope, void* stream);
+int b200unet_gn_bwd_finalize(const double* bstats, const float* coef, const float* gamma, int n, int c, int c_ld,
+                             int groups, int64_t spatial, float* coef2, float* dgamma, float* dbeta, void* stream);
+int b200unet_gn_bwd(const b200unet_tensor* dz, const b200unet_tensor* x, const float* coef, const float* coef2,
+                    const b200unet_tensor* add1, const b200unet_tensor* add2, const b200unet_tensor* dx, void* stream);
+
+/* ---- F.interpolate(scale_factor=2, mode="trilinear", align_corners=False) (decoder.py:105-106), fwd + adjoint */
+int b200unet_upsample2x_fwd(const b200unet_tensor* x, const b200unet_tensor* y, double* stats, int stats_ld,
+                            void* stream);
+int b200unet_upsample2x_bwd(const b200unet_tensor* dy, const b200unet_tensor* dx, void* stream);
+int b200unet_zero_insert(const b200unet_tensor* x, const b200unet_tensor* z, int od, int oh, int ow, void* stream);
+
+/* ---- final 1x1x1 convolution to NCDHW fp32 logits (variational.py:59-60,84-86); act: 0 none 1 sigmoid 2 softmax */
+int b200unet_head_fwd(const b200unet_tensor* x, const float* w, int n_out, int act, float* logits, void* stream);
+int b200unet_head_bwd(const b200unet_tensor* x, const float* w, int n_out, const float* dlogits,
+                      const b200unet_tensor* dx, float* dw, void* stream);
+
+/* ---- Dice criterion (monai.losses.DiceLoss as configured by script_utils.py:61-77).
+ * flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum.
+ * sums: [N][C][3] doubles (I, P, T) written by fwd and consumed by bwd. */
+int b200unet_dice_fwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+                      float smooth_nr, float smooth_dr, double* sums, float* loss, void* stream);
+int b200unet_dice_bwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+                      float smooth_nr, float smooth_dr, const double* sums, const float* grad_out, float* dlogits,
+                      void* stream);
+
+/* ---- whole-network plan: UNet3D forward/backward (segmentation/unet.py:7-50, classification/myronenko.py,
+ * classification/decoder.py:73-130, autoencoder/variational.py:37-87) as one schedule of the kernels above. */
+typedef struct b200unet_net_desc {
+  int32_t n_features, n_outputs, base_width;
+  int32_t n_levels;
+  int32_t encoder_blocks[8];
+  int32_t decoder_blocks[8];
+  int32_t feature_dilation;
+  int32_t norm_groups;
+  int32_t use_transposed_convolutions;
+  int32_t activation;         /* 0 none, 1 sigmoid, 2 softmax (variational.py:62-68) */
+  int32_t split_precision;    /* 0 = bf16 single pass (perf), 1 = hi/lo split, 3 MMAs (parity) */
+  int32_t batch, depth, height, width;
+} b200unet_net_desc;
+
+typedef struct b200unet_plan b200unet_plan;
+
+int b200unet_plan_create(const b200unet_net_desc* desc, b200unet_plan** out);
+void b200unet_plan_destroy(b200unet_plan* plan);
+/* number of parameter tensors, in reference state_dict order */
+int b200unet_plan_num_params(const b200unet_plan* plan);
+/* shape (up to 5 dims, zero padded) and state_dict key of parameter i */
+int b200unet_plan_param_info(const b200unet_plan* plan, int i, int64_t shape[5], char* key, int key_cap);
+size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan);
+/* forward: x NCDHW fp32 -> logits NCDHW fp32.  params: device array-of-pointers (host array of device pointers) to
+ * the fp32 parameters.  dropout_scale: [N][C0] per-channel scale or NULL (eval).  save_for_backward != 0 keeps the
+ * activations needed by b200unet_plan_backward in `workspace`. */
+int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
+                          int save_for_backward, void* workspace, float* logits, void* stream);
+/* backward: dlogits NCDHW fp32 -> grads[i] (fp32, same shapes as params; overwritten). */
+int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const float* const* params, float* const* grads,
+                           void* workspace, void* stream);
+/* number of kernels the last forward / backward call launched (for bench.py's gpu_launches) */
+int b200unet_plan_last_launches(const b200unet_plan* plan);
+
+/* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
+int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UNET_H_ */
