@@ -1,0 +1,82 @@
+"""The C-ABI library: loads, exports every symbol include/b200unet.h declares, and its host-side planner (no GPU
+needed: plan_create is pure host logic) reproduces the reference state-dict contract and rejects what it does not
+implement with an error code instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import UNetConfig, unet3d_state_dict_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200unet.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200unet_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.lib.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    raw = C.CDLL(pkg.lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "missing export: " + name
+    assert set(pkg.lib.EXPORTED_SYMBOLS) == set(declared)      # the binding covers the whole header
+    assert lib.b200unet_version() >= 100
+    assert lib.b200unet_last_error() is not None
+
+
+def test_library_is_sm100a_tcgen05(pkg):
+    """The shipped binary must contain Blackwell tensor-core + TMA SASS (B200_PROFILING.md mnemonics)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")          # no legacy mma.sync path
+
+
+def _plan(pkg, n, d, h, w, **kw):
+    net = pkg.UNet3D(**kw)
+    return net, pkg.models._Plan(net._net_desc(n, d, h, w), torch.device("cpu"))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_features=4, n_outputs=3, base_width=8),
+    dict(n_features=4, n_outputs=3, base_width=32),
+    dict(n_features=1, n_outputs=1, base_width=48, encoder_blocks=[1, 2, 2, 4, 4]),
+    dict(n_features=2, n_outputs=2, base_width=16, encoder_blocks=[2, 2, 1], decoder_blocks=[1, 2, 2]),
+    dict(n_features=4, n_outputs=3, base_width=8, decoder_mirrors_encoder=True),
+])
+def test_plan_param_spec_is_reference_state_dict(pkg, kw):
+    net, plan = _plan(pkg, 1, 32, 32, 32, **kw)
+    okw = {k: v for k, v in kw.items() if k != "decoder_mirrors_encoder"}
+    if kw.get("decoder_mirrors_encoder"):
+        okw["decoder_blocks"] = [1, 2, 2, 4]
+    spec = unet3d_state_dict_spec(UNetConfig(**okw))
+    assert plan.param_spec() == spec
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == spec
+    assert plan.ws_bytes > 0
+
+
+def test_plan_rejects_unsupported_loudly(pkg):
+    net = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8)
+    with pytest.raises(RuntimeError, match="must be even"):
+        pkg.models._Plan(net._net_desc(1, 36, 32, 32), torch.device("cpu"))   # 36 -> 18 -> 9: odd before last level
+    net12 = pkg.UNet3D(n_features=4, n_outputs=3, base_width=12)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        pkg.models._Plan(net12._net_desc(1, 32, 32, 32), torch.device("cpu"))
+
+
+def test_workspace_fits_b200_for_headline_config(pkg):
+    _, plan = _plan(pkg, 2, 128, 128, 128, n_features=4, n_outputs=3, base_width=32)
+    assert plan.ws_bytes < 40 * 2 ** 30                          # 180 GB HBM3e: plenty of headroom
+    _, plan3 = _plan(pkg, 2, 160, 192, 128, n_features=4, n_outputs=3, base_width=32)
+    assert plan3.ws_bytes < 80 * 2 ** 30

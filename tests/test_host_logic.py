@@ -1,0 +1,131 @@
+"""Host-side mirror of the reference interface (CPU only): factories, state-dict handling, error behaviour, the
+step loop and the inference contract.  The CUDA path itself is exercised by the -m gpu tests."""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import UNetConfig, make_state_dict, sliding_window_inference
+from oracle.ref_loader import reference_available, reference_unet3d
+
+
+def test_fetch_model_by_name(pkg):
+    m = pkg.fetch_model_by_name("UNet3D", n_features=4, n_outputs=3, base_width=8)
+    assert isinstance(m, pkg.UNet3D) and m.n_outputs == 3
+    with pytest.raises(ValueError, match="model name NoSuch not supported"):        # build.py:12-13
+        pkg.fetch_model_by_name("NoSuch")
+
+
+def test_ctor_rejects_unimplemented_options(pkg):
+    for kw in (dict(downsampling_stride=3), dict(interpolation_mode="nearest"), dict(kernel_size=5), dict(layer_widths=[8, 16])):
+        with pytest.raises(NotImplementedError):
+            pkg.UNet3D(**kw)
+    with pytest.raises(ValueError):
+        pkg.UNet3D(activation="tanh")
+
+
+def test_no_cpu_fallback(pkg):
+    m = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 16, 16, 16))
+    crit = pkg.DiceLoss(sigmoid=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(torch.zeros(1, 3, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4, dtype=torch.uint8))
+    with pytest.raises(NotImplementedError):
+        pkg.DiceLoss(softmax=True)
+
+
+def test_state_dict_roundtrip_and_build_or_load(pkg, tmp_path):
+    kw = dict(n_features=4, n_outputs=3, base_width=8)
+    sd = make_state_dict(UNetConfig(**kw), seed=7)
+    path = os.path.join(tmp_path, "model.pth")
+    torch.save(sd, path)
+    m = pkg.build_or_load_model("UNet3D", path, n_gpus=0, strict=True, **kw)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # non-strict load tiles/narrows mismatching tensors (build.py:47-64)
+    sd_small = make_state_dict(UNetConfig(n_features=2, n_outputs=3, base_width=8), seed=7)
+    torch.save(sd_small, path)
+    m2 = pkg.build_or_load_model("UNet3D", path, n_gpus=0, strict=False, **kw)
+    w = m2.state_dict()["encoder.layers.0.blocks.0.conv1.conv.weight"]
+    assert w.shape == (8, 4, 3, 3, 3)
+    assert torch.equal(w[:, :2], sd_small["encoder.layers.0.blocks.0.conv1.conv.weight"])
+    assert torch.equal(w[:, 2:], sd_small["encoder.layers.0.blocks.0.conv1.conv.weight"])
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (GPU box)")
+def test_checkpoint_interchange_with_reference(pkg):
+    kw = dict(n_features=4, n_outputs=3, base_width=8)
+    ref = reference_unet3d(**kw)
+    mine = pkg.UNet3D(**kw)
+    mine.load_state_dict(ref.state_dict(), strict=True)           # reference checkpoint -> B200 module
+    ref.load_state_dict(mine.state_dict(), strict=True)           # and back
+    assert list(mine.state_dict()) == list(ref.state_dict())
+
+
+def test_default_init_matches_torch_bounds(pkg):
+    torch.manual_seed(0)
+    m = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8)
+    sd = m.state_dict()
+    w = sd["encoder.layers.1.blocks.0.conv1.conv.weight"]          # [16, 8, 3,3,3]: bound 1/sqrt(8*27)
+    assert float(w.abs().max()) <= (8 * 27) ** -0.5 + 1e-7 and float(w.abs().max()) > 0.9 * (8 * 27) ** -0.5
+    assert torch.all(sd["encoder.layers.0.blocks.0.conv1.norm1.weight"] == 1)
+    assert torch.all(sd["encoder.layers.0.blocks.0.conv1.norm1.bias"] == 0)
+
+
+class _Meta(torch.Tensor):
+    pass
+
+
+def test_volumetric_predictions_contract(pkg):
+    """Re-creation of /root/reference/test/test_predict_volumetric.py's calling contract with a 1x1x1 dummy model."""
+    model = nn.Conv3d(1, 1, kernel_size=1)
+    x = torch.randn(2, 1, 10, 10, 10)
+    with pytest.raises(TypeError):
+        pkg.predict.volumetric_predictions(model, [{"image": x}], "unused")
+    xm = x.as_subclass(_Meta)
+    xm.meta = {}
+    with pytest.raises(KeyError):
+        pkg.predict.volumetric_predictions(model, [{"image": xm}], "unused")
+    xm.meta = {"filename_or_obj": ["a.nii.gz", "b.nii.gz"]}
+    written = []
+    res = pkg.predict.volumetric_predictions(model, [{"image": xm}], "out", activation="sigmoid",
+                                             writer=lambda fn, t, d: written.append((fn, d)))
+    assert [r[0] for r in res] == ["a.nii.gz", "b.nii.gz"] and written == [("a.nii.gz", "out"), ("b.nii.gz", "out")]
+    assert res[0][1].shape == (1, 10, 10, 10)
+    assert float((res[0][1] - torch.sigmoid(model(x))[0]).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["constant", "gaussian"])
+def test_sliding_window_inferer_matches_oracle(pkg, mode):
+    net = nn.Conv3d(2, 3, kernel_size=3, padding=1)
+    x = torch.randn(2, 2, 20, 24, 28, generator=torch.Generator().manual_seed(0))
+    inf = pkg.predict.SlidingWindowInferer(roi_size=(16, 16, 16), sw_batch_size=4, overlap=0.25, mode=mode)
+    with torch.no_grad():
+        got = inf(x, net)
+        ref = sliding_window_inference(x, (16, 16, 16), net, overlap=0.25, mode=mode)
+    assert float((got - ref).abs().max()) < 1e-5
+    built = pkg.predict.build_inferer_from_config({"name": "SlidingWindowInferer", "roi_size": [16, 16, 16]})
+    assert isinstance(built, pkg.predict.SlidingWindowInferer)
+
+
+def test_epoch_training_plumbing_cpu(pkg):
+    """training_utils.py:20-85 call contract with n_gpus=None (the only CPU entry that works in the reference)."""
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Conv3d(2, 3, 1))
+    from oracle import dice_loss
+
+    class Crit(nn.Module):
+        def forward(self, o, t):
+            return dice_loss(o, t)
+    loader = [{"image": torch.randn(2, 2, 4, 4, 4), "label": (torch.rand(2, 3, 4, 4, 4) > 0.5).to(torch.uint8)} for _ in range(3)]
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    before = [p.detach().clone() for p in model.parameters()]
+    synced = []
+    avg = pkg.train.epoch_training(loader, model, Crit(), opt, epoch=0, n_gpus=None, print_frequency=0,
+                                   grad_sync=lambda: synced.append(1))
+    assert 0 < avg < 1 and len(synced) == 3
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    v = pkg.train.epoch_validation(loader, model, Crit(), n_gpus=None)
+    assert 0 < v < 1
