@@ -46,6 +46,16 @@ struct RunCtx {
   const float* drop;
   cudaStream_t st;
   int launches;
+  struct Prof* prof;
+};
+
+enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_NORM, CAT_RESAMPLE, CAT_HEAD, CAT_PACK, CAT_OTHER, CAT_COUNT };
+
+struct Prof {
+  std::vector<cudaEvent_t> ev;    // 2 per launch
+  std::vector<int> cat;
+  size_t used = 0;                // launches recorded
+  bool overflow = false;
 };
 
 struct ConvLayer {
@@ -99,6 +109,8 @@ struct b200unet_plan {
   size_t bz_off = 0, bz_bytes = 0;        // zeroed at the start of every backward (bstats + dw accumulators)
   int last_launches = 0;
   int head_param = -1;
+  Prof* prof = nullptr;
+  double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
   bool have_drop = false;
   std::vector<size_t> stats_allocs;  // deferred: sizes
@@ -257,17 +269,30 @@ static int new_norm(Plan& P, const std::string& prefix, int C, int Cld, long lon
   return (int)P.norms.size() - 1;
 }
 
-#define LAUNCHED(cx, expr) do { B200_TRY(expr); (cx).launches++; } while (0)
+static inline void prof_mark(RunCtx& cx, int cat, bool end) {
+  Prof* p = cx.prof;
+  if (!p) return;
+  if (!end) {
+    if ((p->used + 1) * 2 > p->ev.size()) { p->overflow = true; return; }
+    p->cat[p->used] = cat;
+    cudaEventRecord(p->ev[p->used * 2], cx.st);
+  } else {
+    if (p->overflow) return;
+    cudaEventRecord(p->ev[p->used * 2 + 1], cx.st);
+    p->used++;
+  }
+}
+#define LAUNCHED(cx, cat, expr) do { prof_mark(cx, cat, false); B200_TRY(expr); prof_mark(cx, cat, true); (cx).launches++; } while (0)
 
 // ---- forward op emitters
 static void emit_pack(Plan& P, int ci) {
   P.fwd.push_back([&P, ci](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     const float* w = cx.params[c.pw];
-    LAUNCHED(cx, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 0, reinterpret_cast<bf16*>(cx.ws + c.wf_hi),
+    LAUNCHED(cx, CAT_PACK, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 0, reinterpret_cast<bf16*>(cx.ws + c.wf_hi),
                                      P.split ? reinterpret_cast<bf16*>(cx.ws + c.wf_lo) : nullptr, cx.st));
     if (c.need_dgrad)
-      LAUNCHED(cx, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 1, reinterpret_cast<bf16*>(cx.ws + c.wd_hi),
+      LAUNCHED(cx, CAT_PACK, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 1, reinterpret_cast<bf16*>(cx.ws + c.wd_hi),
                                        P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr, cx.st));
     return OK;
   });
@@ -276,17 +301,24 @@ static void emit_pack(Plan& P, int ci) {
 static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
   P.fwd.push_back([&P, ni, x, y](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
-    LAUNCHED(cx, launch_gn_finalize(stats_ptr(P, cx, x), cx.params[n.pg], cx.params[n.pb], P.d.batch, n.C, n.Cld, n.G,
+    LAUNCHED(cx, CAT_NORM, launch_gn_finalize(stats_ptr(P, cx, x), cx.params[n.pg], cx.params[n.pb], P.d.batch, n.C, n.Cld, n.G,
                                     n.S, 1e-5f, reinterpret_cast<float*>(cx.ws + n.coef), cx.st));
-    LAUNCHED(cx, launch_gn_apply(act_of(P, cx, x), act_of(P, cx, y), reinterpret_cast<float*>(cx.ws + n.coef), 0.f,
+    LAUNCHED(cx, CAT_NORM, launch_gn_apply(act_of(P, cx, x), act_of(P, cx, y), reinterpret_cast<float*>(cx.ws + n.coef), 0.f,
                                  cx.st));
     return OK;
   });
 }
 
 // generic forward-weights conv:  out = (conv(a, W[ci]) [+ conv1x1(a2, W[ci2])] [+ res]) [* dropout]
+static double conv_macs(const Plan& P, int ci, TRef out_like) {
+  const ConvLayer& c = P.convs[ci];
+  const Buf& b = P.bufs[out_like.buf];
+  return (double)b.N * b.D * b.H * b.W * c.Co * c.Ci * c.T;
+}
+
 static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, TRef out, bool stats, bool scale) {
   if (stats) need_stats(P, out.buf);
+  P.macs[CAT_CONV_FWD] += conv_macs(P, ci, out) + (ci2 >= 0 ? conv_macs(P, ci2, out) : 0.0);
   P.fwd.push_back([&P, ci, a, ci2, a2, res, out, stats, scale](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
@@ -310,13 +342,14 @@ static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, T
     if (res.valid()) { r = act_of(P, cx, res); op.res = &r; }
     if (scale && cx.drop) op.scale = cx.drop;
     if (stats) { op.stats = stats_ptr(P, cx, out); op.stats_ld = P.bufs[out.buf].C; }
-    LAUNCHED(cx, launch_igemm_conv(op, cx.st));
+    LAUNCHED(cx, CAT_CONV_FWD, launch_igemm_conv(op, cx.st));
     return OK;
   });
 }
 
 // ---- backward op emitters
 static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
+  P.macs[CAT_CONV_WGRAD] += conv_macs(P, ci, dy);
   P.bwd.push_back([&P, ci, a, dy](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     WgradOp op;
@@ -324,14 +357,15 @@ static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
     op.dy = act_of(P, cx, dy);
     op.ksz = c.ksz; op.stride = c.stride; op.Cip = c.Cip; op.Cop = c.Cop;
     op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
-    LAUNCHED(cx, launch_wgrad(op, cx.st));
+    LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
     return OK;
   });
 }
 
 // data gradient through conv `ci` (stride 1):  out = conv(dy, Wd)  with either the GN/ReLU backward epilogue
 // (ni >= 0, gn_x = raw input of the norm) or a plain epilogue (+res, *dropout scale).
-static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale) {
+static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale, double alg_macs) {
+  P.macs[CAT_CONV_DGRAD] += alg_macs;
   P.bwd.push_back([&P, ci, dy, out, ni, gn_x, res, scale](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
@@ -356,7 +390,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
       op.slope = 0.f;
       op.bstats = reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats);
     }
-    LAUNCHED(cx, launch_igemm_conv(op, cx.st));
+    LAUNCHED(cx, CAT_CONV_DGRAD, launch_igemm_conv(op, cx.st));
     return OK;
   });
 }
@@ -364,7 +398,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
 static void emit_gn_bwd_finalize(Plan& P, int ni) {
   P.bwd.push_back([&P, ni](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
-    LAUNCHED(cx, launch_gn_bwd_finalize(reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats),
+    LAUNCHED(cx, CAT_NORM, launch_gn_bwd_finalize(reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats),
                                         reinterpret_cast<float*>(cx.ws + n.coef), cx.params[n.pg], P.d.batch, n.C, n.Cld,
                                         n.G, n.S, reinterpret_cast<float*>(cx.ws + n.coef2), cx.grads[n.pg],
                                         cx.grads[n.pb], cx.st));
@@ -377,7 +411,7 @@ static void emit_gn_bwd(Plan& P, int ni, TRef dz, TRef x, TRef add1, TRef dx, bo
     const NormLayer& n = P.norms[ni];
     Act a1;
     if (add1.valid()) a1 = act_of(P, cx, add1);
-    LAUNCHED(cx, launch_gn_bwd(act_of(P, cx, dz), act_of(P, cx, x), reinterpret_cast<float*>(cx.ws + n.coef),
+    LAUNCHED(cx, CAT_NORM, launch_gn_bwd(act_of(P, cx, dz), act_of(P, cx, x), reinterpret_cast<float*>(cx.ws + n.coef),
                                reinterpret_cast<float*>(cx.ws + n.coef2), add1.valid() ? &a1 : nullptr, nullptr,
                                act_of(P, cx, dx), (scale && cx.drop) ? cx.drop : nullptr, cx.st));
     return OK;
@@ -420,19 +454,19 @@ static TRef build_block_bwd(Plan& P, const BlockRec& r, TRef dOut) {
   emit_wgrad(P, r.c2, r.a2, dOut);
   if (r.cs >= 0) emit_wgrad(P, r.cs, r.X, dOut);
   TRef dz2 = full(P, new_buf(P, N, D, H, W, C));
-  emit_dgrad(P, r.c2, dOut, dz2, r.n2, r.y1, kNone, false);
+  emit_dgrad(P, r.c2, dOut, dz2, r.n2, r.y1, kNone, false, conv_macs(P, r.c2, dOut));
   emit_gn_bwd_finalize(P, r.n2);
   TRef dy1 = full(P, new_buf(P, N, D, H, W, C));
   emit_gn_bwd(P, r.n2, dz2, r.y1, kNone, dy1, false);
   emit_wgrad(P, r.c1, r.a1, dy1);
   TRef dz1 = full(P, new_buf(P, N, D, H, W, r.X.c));
-  emit_dgrad(P, r.c1, dy1, dz1, r.n1, r.X, kNone, false);
+  emit_dgrad(P, r.c1, dy1, dz1, r.n1, r.X, kNone, false, r.first ? 0.0 : conv_macs(P, r.c1, dy1));
   emit_gn_bwd_finalize(P, r.n1);
   if (r.first) return kNone;
   TRef dX = full(P, new_buf(P, N, D, H, W, r.X.c));
   if (r.cs >= 0) {
     emit_gn_bwd(P, r.n1, dz1, r.X, kNone, dX, false);
-    emit_dgrad(P, r.cs, dOut, dX, -1, kNone, dX, r.scale_in);  // dX = (conv1x1(dOut, Ws^T) + dX) [* scale]
+    emit_dgrad(P, r.cs, dOut, dX, -1, kNone, dX, r.scale_in, conv_macs(P, r.cs, dOut));  // dX = (conv1x1(dOut, Ws^T) + dX) [* scale]
   } else {
     emit_gn_bwd(P, r.n1, dz1, r.X, dOut, dX, r.scale_in);
   }
@@ -468,7 +502,7 @@ static int build(Plan& P) {
   P.fwd.push_back([&P, b_in](RunCtx& cx) -> int {
     B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.stats_off, 0, P.stats_bytes, cx.st));
     TRef t = full(P, b_in);
-    LAUNCHED(cx, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), stats_ptr(P, cx, t), P.bufs[b_in].C, cx.st));
+    LAUNCHED(cx, CAT_RESAMPLE, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), stats_ptr(P, cx, t), P.bufs[b_in].C, cx.st));
     return OK;
   });
 
@@ -534,7 +568,7 @@ static int build(Plan& P) {
     {
       TRef Pin = s.P, U = s.U;
       P.fwd.push_back([&P, Pin, U](RunCtx& cx) -> int {
-        LAUNCHED(cx, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
+        LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
                                            cx.st));
         return OK;
       });
@@ -557,7 +591,7 @@ static int build(Plan& P) {
   const TRef Xfinal = X;
   P.head_param = P.find_param("final_convolution.weight");
   P.fwd.push_back([&P, Xfinal](RunCtx& cx) -> int {
-    LAUNCHED(cx, launch_head_fwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, P.d.activation, cx.logits,
+    LAUNCHED(cx, CAT_HEAD, launch_head_fwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, P.d.activation, cx.logits,
                                  cx.st));
     return OK;
   });
@@ -575,7 +609,7 @@ static int build(Plan& P) {
     g = full(P, new_buf(P, N, xb.D, xb.H, xb.W, Xfinal.c));
     TRef gg = g;
     P.bwd.push_back([&P, Xfinal, gg](RunCtx& cx) -> int {
-      LAUNCHED(cx, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits,
+      LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits,
                                    act_of(P, cx, gg), cx.grads[P.head_param], cx.st));
       return OK;
     });
@@ -591,12 +625,12 @@ static int build(Plan& P) {
     const Buf pb = P.bufs[s.P.buf];
     TRef dP = full(P, new_buf(P, N, pb.D, pb.H, pb.W, out_w));
     P.bwd.push_back([&P, dU, dP](RunCtx& cx) -> int {
-      LAUNCHED(cx, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
+      LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
       return OK;
     });
     emit_wgrad(P, s.cpre, s.Xin, dP);
     TRef gX = full(P, new_buf(P, N, pb.D, pb.H, pb.W, s.Xin.c));
-    emit_dgrad(P, s.cpre, dP, gX, -1, kNone, kNone, false);
+    emit_dgrad(P, s.cpre, dP, gX, -1, kNone, kNone, false, conv_macs(P, s.cpre, dP));
     for (int b = d.decoder_blocks[i] - 1; b >= 0; --b) gX = build_block_bwd(P, dec[i][b], gX);
     g = gX;
   }
@@ -609,13 +643,13 @@ static int build(Plan& P) {
       TRef Z = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
       TRef gin = g;
       P.bwd.push_back([&P, gin, Z](RunCtx& cx) -> int {
-        LAUNCHED(cx, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
+        LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
         return OK;
       });
       TRef gS = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
       // dropout scale belongs to the output of encoder block (0,0): that is this tensor iff level 0 has one block
       const bool sc = (lj == 0 && d.encoder_blocks[0] == 1);
-      emit_dgrad(P, down[lj], Z, gS, -1, kNone, dskip_dec[lj], sc);
+      emit_dgrad(P, down[lj], Z, gS, -1, kNone, dskip_dec[lj], sc, conv_macs(P, down[lj], gin));
       g = gS;
     }
   }
@@ -623,7 +657,7 @@ static int build(Plan& P) {
   for (size_t ci = 0; ci < P.convs.size(); ++ci) {
     P.bwd.push_back([&P, ci](RunCtx& cx) -> int {
       const ConvLayer& c = P.convs[ci];
-      LAUNCHED(cx, launch_unpack_wgrad(reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw), c.Co, c.Ci, c.Cop, c.Cip, c.T, 0,
+      LAUNCHED(cx, CAT_PACK, launch_unpack_wgrad(reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw), c.Co, c.Ci, c.Cop, c.Cip, c.T, 0,
                                        cx.grads[c.pw], cx.st));
       return OK;
     });
@@ -677,6 +711,7 @@ int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* cons
   cx.ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   cx.params = params; cx.x = x; cx.logits = logits;
   cx.st = reinterpret_cast<cudaStream_t>(stream);
+  cx.prof = plan->prof;
   plan->have_drop = dropout_scale != nullptr;
   if (dropout_scale) {
     float* dst = reinterpret_cast<float*>(cx.ws + plan->drop_off);
@@ -697,6 +732,7 @@ int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const floa
   cx.ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   cx.params = params; cx.grads = grads; cx.dlogits = dlogits;
   cx.st = reinterpret_cast<cudaStream_t>(stream);
+  cx.prof = plan->prof;
   if (plan->have_drop) cx.drop = reinterpret_cast<float*>(cx.ws + plan->drop_off);
   for (auto& op : plan->bwd) { int s = op(cx); if (s != OK) return s; }
   plan->last_launches = cx.launches;
@@ -704,5 +740,42 @@ int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const floa
 }
 
 int b200unet_plan_last_launches(const b200unet_plan* plan) { return plan ? plan->last_launches : 0; }
+
+int b200unet_plan_algorithmic_macs(const b200unet_plan* plan, double* macs, int ncat) {
+  if (!plan || !macs) { set_error("algorithmic_macs: null argument"); return E_INVALID; }
+  for (int i = 0; i < ncat; ++i) macs[i] = i < CAT_COUNT ? plan->macs[i] : 0.0;
+  return OK;
+}
+
+int b200unet_plan_profile_begin(b200unet_plan* plan, int max_launches) {
+  if (!plan || max_launches <= 0) { set_error("profile_begin: bad argument"); return E_INVALID; }
+  if (plan->prof) { set_error("profile_begin: already profiling"); return E_INVALID; }
+  Prof* p = new Prof();
+  p->ev.resize((size_t)max_launches * 2);
+  p->cat.resize(max_launches);
+  for (auto& e : p->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { set_error("profile_begin: cudaEventCreate failed"); delete p; return E_CUDA; }
+  plan->prof = p;
+  return OK;
+}
+
+int b200unet_plan_profile_end(b200unet_plan* plan, double* ms_by_cat, int64_t* launches_by_cat, int ncat) {
+  if (!plan || !plan->prof || !ms_by_cat || !launches_by_cat) { set_error("profile_end: not profiling"); return E_INVALID; }
+  Prof* p = plan->prof;
+  plan->prof = nullptr;
+  for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0; launches_by_cat[i] = 0; }
+  int status = p->overflow ? E_INVALID : OK;
+  if (p->overflow) set_error("profile_end: event pool too small");
+  for (size_t i = 0; i < p->used; ++i) {
+    if (cudaEventSynchronize(p->ev[i * 2 + 1]) != cudaSuccess) { status = E_CUDA; set_error("profile_end: event sync failed"); break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p->ev[i * 2], p->ev[i * 2 + 1]);
+    const int c = p->cat[i];
+    if (c < ncat) { ms_by_cat[c] += ms; launches_by_cat[c] += 1; }
+  }
+  for (auto& e : p->ev) cudaEventDestroy(e);
+  delete p;
+  return status;
+}
 
 }  // extern "C"

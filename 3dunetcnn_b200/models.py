@@ -68,6 +68,22 @@ class _Plan:
     def last_launches(self) -> int:
         return int(self.lib.b200unet_plan_last_launches(self.handle))
 
+    CATEGORIES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "norm_act", "resample", "head", "weight_pack", "other")
+
+    def algorithmic_macs(self):
+        arr = (C.c_double * 8)()
+        _lib.check(self.lib.b200unet_plan_algorithmic_macs(self.handle, arr, 8), "algorithmic_macs")
+        return dict(zip(self.CATEGORIES, [float(v) for v in arr]))
+
+    def profile_begin(self, max_launches: int) -> None:
+        _lib.check(self.lib.b200unet_plan_profile_begin(self.handle, int(max_launches)), "profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        _lib.check(self.lib.b200unet_plan_profile_end(self.handle, ms, cnt, 8), "profile_end")
+        return {k: {"ms": float(m), "launches": int(c)} for k, m, c in zip(self.CATEGORIES, ms, cnt)}
+
     def __del__(self):
         try:
             if self.handle:

@@ -153,6 +153,15 @@ int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const floa
 /* number of kernels the last forward / backward call launched (for bench.py's gpu_launches) */
 int b200unet_plan_last_launches(const b200unet_plan* plan);
 
+/* per-category accounting for bench.py's roofline (categories: 0 conv fwd, 1 conv dgrad, 2 conv wgrad, 3 norm/act,
+ * 4 resample/pack-input, 5 head, 6 weight pack/unpack, 7 other).  algorithmic_macs: conv MACs of ONE forward+backward
+ * pass (dgrad excludes the convolutions that read the network input; stride-2 dgrad counted at its true size).
+ * profile_begin/end bracket any number of forward/backward calls: every launch is timed with a CUDA-event pair on
+ * the launching stream; profile_end synchronises those events and returns summed milliseconds and launch counts. */
+int b200unet_plan_algorithmic_macs(const b200unet_plan* plan, double* macs, int ncat);
+int b200unet_plan_profile_begin(b200unet_plan* plan, int max_launches);
+int b200unet_plan_profile_end(b200unet_plan* plan, double* ms_by_cat, int64_t* launches_by_cat, int ncat);
+
 /* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
 int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
 
