@@ -1,0 +1,340 @@
+// Halo-resident implicit-GEMM convolution (3x3x3, stride 1) for sm_100a: the successor of igemm_conv.cu's per-tap
+// streaming kernel for every layer whose output plane is at least 8 x 16.
+//
+// A CTA (persistent, one per SM) walks output tiles of 8(w) x 16(h) x TD(d) voxels.  For each K chunk of KC input
+// channels it TMA-loads ONE halo box (KC, 10, 18, TD+2) of the activation into shared memory and then serves all 27
+// taps from it: tap (kd,kh,kw) of output plane d is the UMMA A operand whose descriptor START ADDRESS is shifted by
+// ((d+kd)*18 + kh)*10 + kw rows and whose 8-row-group stride (SBO) is one halo row of 10 voxels.  The hardware
+// applies the 128B/64B/32B swizzle on absolute shared-memory address bits (verified by csrc/probe.cu on B200, see
+// profiles/probe_r01.txt), so shifted / re-strided descriptors read exactly what TMA wrote.  L2->SM traffic for the
+// activation drops from 27 reads per voxel (streaming kernel) to (TD+2)/TD * 1.41.
+// Weights stream through a small ring: one (KC x BN) tile per (chunk, tap), each reused by TD output planes, i.e.
+// TD accumulators of 128 x BN fp32 live in TMEM.  With 2 accumulator sets (when 2*TD*BN <= 512 columns) the epilogue
+// of tile i overlaps the MMAs of tile i+1; two halo buffers let the next chunk/tile load under the current MMAs.
+// The optional second source (the residual block's 1x1x1 `sample`) is one more halo box read at its centre tap.
+// Epilogue: shared with igemm_conv.cu (conv_common.cuh).
+#include <cstdlib>
+#include "conv_common.cuh"
+
+namespace b200 {
+
+template <int KC, int BN, int TD>
+struct HaloCfg {
+  static constexpr int RB = KC * 2;                         // bytes per voxel row
+  static constexpr int HALO_ROWS = 180 * (TD + 2);          // 10 x 18 x (TD+2)
+  static constexpr int HALO_TX = HALO_ROWS * RB;
+  static constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;
+  static constexpr int NHALO = 2;
+  static constexpr int B_TX = BN * KC * 2;
+  static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
+  static constexpr int NB = 8;
+  static constexpr int NACC = (2 * TD * BN <= 512) ? 2 : 1;
+  static constexpr int ACC_COLS = NACC * TD * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;
+  static constexpr int SMEM_BYTES = NHALO * HALO_BYTES + NB * B_BYTES + AUX_BYTES + 1024;
+  static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
+  static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
+  static constexpr uint32_t SBO_B = 8 * RB;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
+};
+
+struct HaloArgs {
+  int tiles_total;   // N * tiles_d * tiles_h * tiles_w * ntiles
+  int ntiles;        // output-channel tiles
+};
+
+template <int KC, int BN, int TD>
+__global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
+                                                      const HaloArgs hp) {
+  using Cfg = HaloCfg<KC, BN, TD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_halo = smem;
+  uint8_t* smem_b = smem + Cfg::NHALO * Cfg::HALO_BYTES;
+  uint8_t* aux = smem_b + Cfg::NB * Cfg::B_BYTES;
+  uint64_t* halo_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* halo_empty = halo_full + Cfg::NHALO;
+  uint64_t* b_full = halo_empty + Cfg::NHALO;
+  uint64_t* b_empty = b_full + Cfg::NB;
+  uint64_t* acc_full = b_empty + Cfg::NB;
+  uint64_t* acc_empty = acc_full + Cfg::NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::NACC);
+  float* s_stats = reinterpret_cast<float*>(aux + 1024);
+  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + BN * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0][0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
+      for (int s = 0; s < Cfg::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+      for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // K groups of one tile: source 0 = 27 taps per chunk, source 1 (optional 1x1x1) = centre tap per chunk
+  const int groups0 = p.kchunks[0], groups1 = p.ntaps[1] ? p.kchunks[1] : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t hi = 0, bi = 0;
+      for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % hp.ntiles; t /= hp.ntiles;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int dt = t % p.tiles_d;
+        const int n = t / p.tiles_d;
+        const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
+        for (int g = 0; g < groups0 + groups1; ++g) {
+          const int src = g < groups0 ? 0 : 1;
+          const int kc = src == 0 ? g : g - groups0;
+          const int ntap = src == 0 ? 27 : 1;
+          for (int pass = 0; pass < p.npass; ++pass) {
+            {
+              const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
+              mbar_wait(&halo_empty[s], ph ^ 1);
+              mbar_expect_tx(&halo_full[s], Cfg::HALO_TX);
+              tma_load_5d(smem_halo + s * Cfg::HALO_BYTES, &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1,
+                          h0 - 1, d0 - 1, n);
+              ++hi;
+            }
+            for (int tap = 0; tap < ntap; ++tap) {
+              const uint32_t s = bi % Cfg::NB, ph = (bi / Cfg::NB) & 1;
+              mbar_wait(&b_empty[s], ph ^ 1);
+              mbar_expect_tx(&b_full[s], Cfg::B_TX);
+              tma_load_3d(smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, tap);
+              ++bi;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      uint32_t hi = 0, bi = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti % Cfg::NACC;
+        mbar_wait(&acc_empty[as], ((ti / Cfg::NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + as * TD * BN;
+        bool first = true;
+        for (int g = 0; g < groups0 + groups1; ++g) {
+          const int src = g < groups0 ? 0 : 1;
+          const int ntap = src == 0 ? 27 : 1;
+          for (int pass = 0; pass < p.npass; ++pass) {
+            const uint32_t hs = hi % Cfg::NHALO;
+            mbar_wait(&halo_full[hs], (hi / Cfg::NHALO) & 1);
+            const uint32_t halo_addr = smem_u32(smem_halo + hs * Cfg::HALO_BYTES);
+            for (int tap = 0; tap < ntap; ++tap) {
+              const int tt = src == 0 ? tap : 13;
+              const int kd = tt / 9, kh = (tt / 3) % 3, kw = tt % 3;
+              const uint32_t bs = bi % Cfg::NB;
+              mbar_wait(&b_full[bs], (bi / Cfg::NB) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(smem_b + bs * Cfg::B_BYTES);
+#pragma unroll
+              for (int dpl = 0; dpl < TD; ++dpl) {
+                const uint32_t a_addr = halo_addr + (((dpl + kd) * 18 + kh) * 10 + kw) * Cfg::RB;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Cfg::SBO_A, Cfg::LAYOUT);
+                  const uint64_t db = make_smem_desc(b_addr + k * 32, 16, Cfg::SBO_B, Cfg::LAYOUT);
+                  umma_bf16(acc0 + dpl * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(&b_empty[bs]);
+              ++bi;
+            }
+            umma_commit(&halo_empty[hs]);
+            ++hi;
+          }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    const int e = threadIdx.x - 64;
+    const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
+    uint32_t ti = 0;
+    int coef_n = -1, coef_n0 = -1;
+    for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int nt = t % hp.ntiles; t /= hp.ntiles;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int dt = t % p.tiles_d;
+      const int n = t / p.tiles_d;
+      const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
+      // per-tile shared state: zero the statistics, (re)load the GN coefficients when (n, n0) changes
+      for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
+      if (p.mode == 1 && (n != coef_n || n0 != coef_n0)) {
+        for (int c = e; c < BN; c += 128)
+          s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        coef_n = n; coef_n0 = n0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t as = ti % Cfg::NACC;
+      mbar_wait(&acc_full[as], (ti / Cfg::NACC) & 1);
+      tc_fence_after();
+      const int w = w0 + (row & 7), h = h0 + (row >> 3);
+#pragma unroll 1
+      for (int dpl = 0; dpl < TD; ++dpl) {
+        const int d = d0 + dpl;
+        const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
+        const long long vox = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+        conv_epilogue_tile<BN>(p, tmem_base + (as * TD + dpl) * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef,
+                               want_stats);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);      // accumulator set drained: MMA may overwrite it
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // all partial sums are in s_stats
+      if (want_stats) {
+        double* dst = (p.mode == 0) ? p.stats : p.bstats;
+        const int ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
+        for (int c = e; c < BN; c += 128) {
+          if (n0 + c < p.Cout) {
+            atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
+            atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // flushed before the next tile zeroes s_stats
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int KC, int BN, int TD>
+static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, const HaloArgs& h, int grid, cudaStream_t st) {
+  using Cfg = HaloCfg<KC, BN, TD>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  k_conv_halo<KC, BN, TD><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a, h);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+bool conv_halo_eligible(const ConvOp& op) {
+  if (op.src[0].ksz != 3 || op.src[0].stride != 1) return false;
+  if (op.nsrc == 2 && (op.src[1].ksz != 1 || op.src[1].stride != 1)) return false;
+  return op.out.W >= 8 && op.out.H >= 16;
+}
+
+int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
+  const Act& out = op.out;
+  B200_REQUIRE(conv_halo_eligible(op), E_UNSUPPORTED, "conv_halo: shape not eligible");
+  B200_REQUIRE(out.C % 8 == 0 && out.ld % 8 == 0, E_UNSUPPORTED, "conv_halo: Cout=%d must be a multiple of 8", out.C);
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  a.N = out.N; a.Do = out.D; a.Ho = out.H; a.Wo = out.W; a.Cout = out.C;
+  int cin_max = 0;
+  bool split = false;
+  for (int s = 0; s < op.nsrc; ++s) {
+    const ConvSrc& c = op.src[s];
+    B200_REQUIRE(c.x.C % 8 == 0 && c.x.ld % 8 == 0, E_UNSUPPORTED, "conv_halo: Cin=%d must be a multiple of 8", c.x.C);
+    B200_REQUIRE(c.x.N == out.N && c.x.D == out.D && c.x.H == out.H && c.x.W == out.W, E_INVALID,
+                 "conv_halo: source %d extent mismatch", s);
+    if (c.x.C > cin_max) cin_max = c.x.C;
+    if (c.x.lo || c.w_lo) split = true;
+  }
+  if (split)
+    for (int s = 0; s < op.nsrc; ++s)
+      B200_REQUIRE(op.src[s].x.lo && op.src[s].w_lo, E_INVALID, "conv_halo: split mode needs lo parts on every source");
+  const int KC = cin_max > 16 ? 32 : 16;
+  int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
+  if (const char* e = getenv("B200UNET_HALO_BN")) {   // tuning override: cap the N tile
+    const int v = atoi(e);
+    if ((v == 16 || v == 32 || v == 64 || v == 128) && v < BN) BN = v;
+  }
+  const int ntiles = ceil_div(out.C, BN);
+  // TD: deepest tile that still gives every SM work (>= ~2 tiles per SM), bounded by TMEM (TD*BN <= 512)
+  int TD = 4;
+  auto tiles_for = [&](int td) { return (long long)out.N * ceil_div(out.D, td) * ceil_div(out.H, 16) * ceil_div(out.W, 8) * ntiles; };
+  while (TD > 1 && (tiles_for(TD) < 2LL * num_sms || out.D < TD)) TD >>= 1;
+  if (const char* e = getenv("B200UNET_HALO_TD")) {   // tuning override (1, 2 or 4)
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && v * BN <= 512) TD = v;
+  }
+  a.tw = 8; a.th = 16; a.td = TD;
+  a.tiles_w = ceil_div(out.W, 8); a.tiles_h = ceil_div(out.H, 16); a.tiles_d = ceil_div(out.D, TD);
+  const Swz swz = swz_for_bytes(KC * 2);
+  for (int s = 0; s < op.nsrc; ++s) {
+    const ConvSrc& c = op.src[s];
+    a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = 1;
+    a.kchunks[s] = ceil_div(c.x.C, KC);
+    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18, TD + 2, 1, swz));
+    B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+    if (split) {
+      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18, TD + 2, 1, swz));
+      B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+    }
+  }
+  a.npass = split ? 3 : 1;
+  a.mode = op.mode;
+  a.out_hi = out.hi; a.out_lo = out.lo; a.ldo = out.ld;
+  if (op.res) {
+    B200_REQUIRE(op.res->C == out.C, E_INVALID, "conv_halo: residual channel mismatch");
+    a.res_hi = op.res->hi; a.res_lo = op.res->lo; a.ldr = op.res->ld;
+  }
+  a.scale = op.scale;
+  a.stats = op.stats; a.stats_ld = op.stats_ld;
+  if (op.mode == 1) {
+    B200_REQUIRE(op.gn_x && op.coef, E_INVALID, "conv_halo: mode 1 needs gn_x and coef");
+    B200_REQUIRE(op.gn_x->C == out.C, E_INVALID, "conv_halo: gn_x channel mismatch");
+    a.x_hi = op.gn_x->hi; a.x_lo = op.gn_x->lo; a.ldx = op.gn_x->ld;
+    a.coef = reinterpret_cast<const float4*>(op.coef); a.coef_ld = op.coef_ld;
+    a.slope = op.slope; a.bstats = op.bstats;
+  }
+  HaloArgs h;
+  h.ntiles = ntiles;
+  h.tiles_total = (int)tiles_for(TD);
+  const int grid = h.tiles_total < num_sms ? h.tiles_total : num_sms;
+#define B200_HALO_CASE(kc, bn, td) \
+  if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td>(maps, a, h, grid, st);
+  B200_HALO_CASE(16, 16, 4) B200_HALO_CASE(16, 16, 2) B200_HALO_CASE(16, 16, 1)
+  B200_HALO_CASE(16, 32, 4) B200_HALO_CASE(16, 32, 2) B200_HALO_CASE(16, 32, 1)
+  B200_HALO_CASE(16, 64, 4) B200_HALO_CASE(16, 64, 2) B200_HALO_CASE(16, 64, 1)
+  B200_HALO_CASE(16, 128, 4) B200_HALO_CASE(16, 128, 2) B200_HALO_CASE(16, 128, 1)
+  B200_HALO_CASE(32, 16, 4) B200_HALO_CASE(32, 16, 2) B200_HALO_CASE(32, 16, 1)
+  B200_HALO_CASE(32, 32, 4) B200_HALO_CASE(32, 32, 2) B200_HALO_CASE(32, 32, 1)
+  B200_HALO_CASE(32, 64, 4) B200_HALO_CASE(32, 64, 2) B200_HALO_CASE(32, 64, 1)
+  B200_HALO_CASE(32, 128, 4) B200_HALO_CASE(32, 128, 2) B200_HALO_CASE(32, 128, 1)
+#undef B200_HALO_CASE
+  set_error("conv_halo: no kernel for KC=%d BN=%d TD=%d", KC, BN, TD);
+  return E_UNSUPPORTED;
+}
+
+}  // namespace b200

@@ -65,7 +65,10 @@ struct ConvOp {
   double* bstats;      // mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat)
 };
 
-int launch_igemm_conv(const ConvOp& op, cudaStream_t st);
+int launch_igemm_conv(const ConvOp& op, cudaStream_t st);   // dispatcher: halo-resident kernel when eligible
+int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st);
+bool conv_halo_eligible(const ConvOp& op);
+int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st);
 
 // ---- tensor-core weight gradient (wgrad.cu):  dW[t][ci][co] += sum_v dy[v][co] * a[v*stride + t - pad][ci]
 struct WgradOp {

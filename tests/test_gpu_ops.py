@@ -32,6 +32,10 @@ def _packed_to_torch(L, w, mode, split, cout, cin, ksz):
     (256, 256, (4, 4, 8), 3, 1), (24, 40, (5, 7, 9), 3, 1), (96, 192, (4, 4, 8), 3, 1), (64, 32, (8, 8, 8), 3, 1),
     (256, 128, (4, 4, 8), 1, 1), (8, 32, (6, 6, 6), 1, 1), (32, 32, (16, 16, 16), 3, 2), (64, 64, (8, 8, 8), 3, 2),
     (16, 16, (10, 6, 14), 3, 2),
+    # output plane >= 8 x 16 -> halo-resident kernel (conv_halo.cu); smaller planes -> streaming kernel (igemm_conv.cu)
+    (32, 32, (8, 16, 16), 3, 1), (64, 32, (4, 16, 8), 3, 1), (8, 32, (16, 16, 16), 3, 1), (128, 128, (8, 16, 8), 3, 1),
+    (256, 256, (2, 16, 8), 3, 1), (24, 40, (6, 18, 12), 3, 1), (96, 192, (3, 16, 8), 3, 1), (32, 64, (5, 24, 20), 3, 1),
+    (16, 16, (1, 16, 8), 3, 1),
 ])
 def test_conv3d_forward(pkg, cin, cout, dims, ksz, stride, split):
     L = pkg.lib
@@ -71,7 +75,7 @@ def test_conv3d_fused_epilogue_residual_dropout_stats_concat_slice(pkg, split):
     per-channel statistics the next GroupNorm consumes."""
     L = pkg.lib
     torch.manual_seed(1)
-    n, ci, co, D = 2, 32, 32, 8
+    n, ci, co, D = 2, 32, 32, 16          # 16^3: halo-resident kernel
     x = torch.randn(n, ci, D, D, D, device=DEV)
     w = torch.randn(co, ci, 3, 3, 3, device=DEV) / (ci * 27) ** 0.5
     r = torch.randn(n, co, D, D, D, device=DEV)
@@ -92,11 +96,13 @@ def test_conv3d_fused_epilogue_residual_dropout_stats_concat_slice(pkg, split):
 
 
 @pytest.mark.parametrize("split", [False, True])
-def test_conv3d_two_sources_is_block_output(pkg, split):
-    """conv2(a2) + sample(x): the residual block's second conv with the 1x1x1 `sample` as a second K-slab."""
+@pytest.mark.parametrize("D", [8, 16])
+def test_conv3d_two_sources_is_block_output(pkg, split, D):
+    """conv2(a2) + sample(x): the residual block's second conv with the 1x1x1 `sample` as a second K-slab
+    (D=8: streaming kernel, D=16: halo-resident kernel)."""
     L = pkg.lib
     torch.manual_seed(2)
-    n, ci, co, D = 1, 8, 32, 8
+    n, ci, co = 1, 8, 32
     x = torch.randn(n, ci, D, D, D, device=DEV)
     h = torch.randn(n, co, D, D, D, device=DEV)
     w2 = torch.randn(co, co, 3, 3, 3, device=DEV) / (co * 27) ** 0.5
@@ -111,11 +117,12 @@ def test_conv3d_two_sources_is_block_output(pkg, split):
 
 
 @pytest.mark.parametrize("split", [False, True])
-def test_conv3d_dgrad_groupnorm_relu_backward_epilogue(pkg, split):
+@pytest.mark.parametrize("D", [8, 16])
+def test_conv3d_dgrad_groupnorm_relu_backward_epilogue(pkg, split, D):
     """dz = dgrad(dy) masked by ReLU'(GN(x)), plus per-channel (sum dz, sum dz*xhat): checked against autograd."""
     L = pkg.lib
     torch.manual_seed(3)
-    n, ci, co, D, G = 2, 32, 64, 8, 8
+    n, ci, co, G = 2, 32, 64, 8
     dyv = torch.randn(n, co, D, D, D, device=DEV)
     xv = torch.randn(n, ci, D, D, D, device=DEV) + 0.3
     w = torch.randn(co, ci, 3, 3, 3, device=DEV) / (ci * 27) ** 0.5

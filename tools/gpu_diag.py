@@ -252,12 +252,18 @@ def group_conv():
         (96, 192, (4, 4, 8), 3, 1, False), (64, 128, (8, 8, 8), 1, 1, False), (256, 128, (4, 4, 8), 1, 1, False),
         (32, 32, (16, 16, 16), 3, 2, False), (64, 64, (8, 8, 8), 3, 2, False), (8, 8, (8, 8, 8), 3, 2, False),
         (32, 32, (5, 7, 9), 3, 1, False),
+        # halo-resident kernel (output plane >= 8 x 16)
+        (32, 32, (8, 16, 16), 3, 1, False), (64, 32, (4, 16, 8), 3, 1, False), (8, 32, (16, 16, 16), 3, 1, False),
+        (128, 128, (8, 16, 8), 3, 1, False), (256, 256, (2, 16, 8), 3, 1, False), (24, 40, (6, 18, 12), 3, 1, False),
+        (96, 192, (3, 16, 8), 3, 1, False), (32, 64, (5, 24, 20), 3, 1, False), (16, 16, (1, 16, 8), 3, 1, False),
+        (32, 32, (8, 16, 16), 3, 1, True), (128, 128, (4, 16, 8), 3, 1, True),
         (64, 64, (8, 8, 8), 3, 1, True), (32, 64, (8, 8, 8), 3, 1, True), (8, 8, (8, 8, 8), 3, 1, True),
         (32, 32, (8, 8, 8), 3, 2, True),
     ]
     for c in cases:
         run("conv %s" % (c,), lambda c=c: conv_case(*c))
-    for c in [(32, 32, (8, 8, 8), 3, 1, False), (64, 128, (8, 8, 8), 3, 1, True)]:
+    for c in [(32, 32, (8, 8, 8), 3, 1, False), (64, 128, (8, 8, 8), 3, 1, True), (32, 32, (8, 16, 16), 3, 1, False),
+              (64, 128, (4, 16, 16), 3, 1, True)]:
         run("conv extras %s" % (c,), lambda c=c: conv_case(*c, extras=True))
 
     def t_two_src():
