@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
   const int groups0 = p.kchunks[0], groups1 = p.ntaps[1] ? p.kchunks[1] : 0;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
+    {
+      const uint32_t issue = elect_one() ? 1u : 0u;
       uint32_t hi = 0, bi = 0;
       for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x) {
         int t = tile;
@@ -110,16 +111,16 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
             {
               const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
               mbar_wait(&halo_empty[s], ph ^ 1);
-              mbar_expect_tx(&halo_full[s], Cfg::HALO_TX);
-              tma_load_5d(smem_halo + s * Cfg::HALO_BYTES, &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1,
-                          h0 - 1, d0 - 1, n);
+              mbar_expect_tx_if(issue, &halo_full[s], Cfg::HALO_TX);
+              tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES, &maps.a[src][pass == 1], &halo_full[s], kc * KC,
+                             w0 - 1, h0 - 1, d0 - 1, n);
               ++hi;
             }
             for (int tap = 0; tap < ntap; ++tap) {
               const uint32_t s = bi % Cfg::NB, ph = (bi / Cfg::NB) & 1;
               mbar_wait(&b_empty[s], ph ^ 1);
-              mbar_expect_tx(&b_full[s], Cfg::B_TX);
-              tma_load_3d(smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, tap);
+              mbar_expect_tx_if(issue, &b_full[s], Cfg::B_TX);
+              tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, tap);
               ++bi;
             }
           }
@@ -127,49 +128,53 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-convergent, one lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT);
+      constexpr uint32_t hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT);
+      const uint32_t issue = elect_one() ? 1u : 0u;
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t halo0 = smem_u32(smem_halo), b0 = smem_u32(smem_b);
       uint32_t hi = 0, bi = 0, ti = 0;
       for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
         const uint32_t as = ti % Cfg::NACC;
         mbar_wait(&acc_empty[as], ((ti / Cfg::NACC) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + as * TD * BN;
-        bool first = true;
+        const uint32_t acc0 = tmem0 + as * TD * BN;
+        uint32_t first = 1;
         for (int g = 0; g < groups0 + groups1; ++g) {
           const int src = g < groups0 ? 0 : 1;
           const int ntap = src == 0 ? 27 : 1;
           for (int pass = 0; pass < p.npass; ++pass) {
             const uint32_t hs = hi % Cfg::NHALO;
             mbar_wait(&halo_full[hs], (hi / Cfg::NHALO) & 1);
-            const uint32_t halo_addr = smem_u32(smem_halo + hs * Cfg::HALO_BYTES);
+            const uint32_t halo_lo = desc_lo(halo0 + hs * Cfg::HALO_BYTES, 16);
             for (int tap = 0; tap < ntap; ++tap) {
               const int tt = src == 0 ? tap : 13;
               const int kd = tt / 9, kh = (tt / 3) % 3, kw = tt % 3;
               const uint32_t bs = bi % Cfg::NB;
               mbar_wait(&b_full[bs], (bi / Cfg::NB) & 1);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(smem_b + bs * Cfg::B_BYTES);
+              const uint32_t b_lo = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
+              const uint32_t a_lo = halo_lo + (((kd * 18 + kh) * 10 + kw) * Cfg::RB >> 4);
 #pragma unroll
               for (int dpl = 0; dpl < TD; ++dpl) {
-                const uint32_t a_addr = halo_addr + (((dpl + kd) * 18 + kh) * 10 + kw) * Cfg::RB;
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Cfg::SBO_A, Cfg::LAYOUT);
-                  const uint64_t db = make_smem_desc(b_addr + k * 32, 16, Cfg::SBO_B, Cfg::LAYOUT);
-                  umma_bf16(acc0 + dpl * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                  umma_bf16_if(issue, acc0 + dpl * BN, desc_from(a_lo + ((dpl * 180 * Cfg::RB + k * 32) >> 4), hi_a),
+                               desc_from(b_lo + (k * 32 >> 4), hi_b), idesc, (k == 0) ? (first ^ 1u) : 1u);
                 }
               }
-              first = false;
-              umma_commit(&b_empty[bs]);
+              first = 0;
+              umma_commit_if(issue, &b_empty[bs]);
               ++bi;
             }
-            umma_commit(&halo_empty[hs]);
+            umma_commit_if(issue, &halo_empty[hs]);
             ++hi;
           }
         }
-        umma_commit(&acc_full[as]);
+        umma_commit_if(issue, &acc_full[as]);
       }
     }
   } else {
@@ -246,6 +251,10 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, const HaloAr
 }
 
 bool conv_halo_eligible(const ConvOp& op) {
+  // measured on B200 (profiles/r01_convbench.txt): the halo-resident kernel wins for Cin <= 64 (operand-bandwidth
+  // bound layers); for Cin >= 128 the streaming kernel's deeper K per tile is faster.
+  static const int max_c = getenv("B200UNET_HALO_MAXC") ? atoi(getenv("B200UNET_HALO_MAXC")) : 64;
+  if (op.src[0].x.C > max_c) return false;
   if (op.src[0].ksz != 3 || op.src[0].stride != 1) return false;
   if (op.nsrc == 2 && (op.src[1].ksz != 1 || op.src[1].stride != 1)) return false;
   return op.out.W >= 8 && op.out.H >= 16;

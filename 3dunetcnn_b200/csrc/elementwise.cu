@@ -400,11 +400,23 @@ __global__ void k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int s
     for (int j = 0; j < 8; ++j) { a[j] += o[j]; b[j] += o[j] * o[j]; }
   }
   if (stats) {
-    if (my_c8 >= 0) {
+    const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;   // then lanes l, l' share the chunk iff l % c8n == l' % c8n
+    const int lane_c8 = threadIdx.x % c8n;                    // == my_c8 for every thread that did work
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 0], a[j]);
-        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 1], b[j]);
+    for (int j = 0; j < 8; ++j) {
+      float pa = a[j], pb = b[j];
+      if (pow2) {
+        for (int off = 16; off >= c8n; off >>= 1) {
+          pa += __shfl_xor_sync(0xffffffffu, pa, off);
+          pb += __shfl_xor_sync(0xffffffffu, pb, off);
+        }
+        if ((threadIdx.x & 31) < c8n) {
+          atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 0], pa);
+          atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 1], pb);
+        }
+      } else if (my_c8 >= 0) {
+        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 0], pa);
+        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 1], pb);
       }
     }
     __syncthreads();
@@ -523,57 +535,88 @@ int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float
 }
 
 // dx[v][c] = sum_o dlogits[n][o][s] * w[o][c] ;  dw[o][c] += sum_v dlogits[o] * x[v][c]
-__global__ void k_head_bwd(Act x, const float* __restrict__ w, int n_out, const float* __restrict__ dlogits, Act dx,
+// thread <-> (voxel, 8-channel chunk): the chunk is fixed per thread across the grid-stride loop, so the dw partials
+// (n_out x 8) stay in registers and are reduced once at the end (shuffle over lanes that share the chunk -> smem -> global).
+template <int NO>
+__global__ void k_head_bwd(Act x, const float* __restrict__ w, const float* __restrict__ dlogits, Act dx,
                            float* __restrict__ dw) {
-  extern __shared__ float sm[];  // sw [n_out][C] | sdw [n_out][C]
+  extern __shared__ float sm[];  // sw [NO][C] | sdw [NO][C]
   float* sw = sm;
-  float* sdw = sm + n_out * x.C;
-  for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  float* sdw = sm + NO * x.C;
+  for (int i = threadIdx.x; i < NO * x.C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
   __syncthreads();
+  const int c8n = x.C / 8;
   const long long S = (long long)x.D * x.H * x.W;
-  const long long total = x.N * S;
-  const int lane = threadIdx.x & 31;
-  for (long long v0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); v0 < total;
-       v0 += (long long)gridDim.x * blockDim.x) {
-    const long long v = v0 + lane;
-    const bool ok = v < total;
-    float g[8];
+  const long long total = (long long)x.N * S * c8n;
+  const int c8 = threadIdx.x % c8n;   // blockDim.x % c8n == 0 and the grid stride is a multiple of blockDim.x
+  float pdw[NO][8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) g[o] = 0.f;
-    if (ok) {
-      const int n = (int)(v / S);
-      const long long s = v % S;
-      for (int o = 0; o < n_out; ++o) g[o] = dlogits[((long long)n * n_out + o) * S + s];
-    }
-    for (int c0 = 0; c0 < x.C; c0 += 8) {
-      float u[8], d[8];
+  for (int o = 0; o < NO; ++o)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { u[j] = 0.f; d[j] = 0.f; }
-      if (ok) load8(x.hi, x.lo, v * x.ld + c0, u);
+    for (int j = 0; j < 8; ++j) pdw[o][j] = 0.f;
+  float wr[NO][8];
 #pragma unroll
-      for (int o = 0; o < 8; ++o)
-        if (o < n_out) {
+  for (int o = 0; o < NO; ++o)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            d[j] = fmaf(g[o], sw[o * x.C + c0 + j], d[j]);
-            float p = warp_sum(g[o] * u[j]);
-            if (lane == 0) atomicAdd(&sdw[o * x.C + c0 + j], p);
-          }
-        }
-      if (ok) store8(dx.hi, dx.lo, v * dx.ld + c0, d);
-    }
+    for (int j = 0; j < 8; ++j) wr[o][j] = sw[o * x.C + c8 * 8 + j];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / c8n;
+    const int n = (int)(v / S);
+    const long long s = v % S;
+    float g[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) g[o] = __ldg(dlogits + ((long long)n * NO + o) * S + s);
+    float u[8], d[8];
+    load8(x.hi, x.lo, v * x.ld + c8 * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = fmaf(g[o], wr[o][j], d[j]);
+        pdw[o][j] = fmaf(g[o], u[j], pdw[o][j]);
+      }
+    store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
   }
+  // lanes l and l' share the chunk iff l % c8n == l' % c8n (c8n is a power of two <= 32 here, else fall back to atomics)
+  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
+#pragma unroll
+  for (int o = 0; o < NO; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = pdw[o][j];
+      if (pow2) {
+        for (int off = 16; off >= c8n; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+        if ((threadIdx.x & 31) < c8n) atomicAdd(&sdw[o * x.C + c8 * 8 + j], p);
+      } else {
+        atomicAdd(&sdw[o * x.C + c8 * 8 + j], p);
+      }
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+  for (int i = threadIdx.x; i < NO * x.C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
 }
 
 int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
                     cudaStream_t st) {
   B200_REQUIRE(n_out >= 1 && n_out <= 8, E_UNSUPPORTED, "head_bwd: n_outputs=%d > 8 unsupported", n_out);
+  B200_REQUIRE(x.C % 8 == 0 && dx.C == x.C, E_INVALID, "head_bwd: channel mismatch");
   B200_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * x.C, st));
-  int blocks = ew_blocks(x.voxels(), 256);
-  if (blocks > 592) blocks = 592;
-  k_head_bwd<<<blocks, 256, 2 * n_out * x.C * sizeof(float), st>>>(x, w, n_out, dlogits, dx, dw);
+  const int c8n = x.C / 8;
+  int threads = 256;
+  while (threads % c8n) threads += 32;
+  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "head_bwd: C=%d unsupported", x.C);
+  long long total = x.voxels() * c8n;
+  int blocks = ew_blocks(total, threads);
+  if (blocks > 1184) blocks = 1184;
+  const size_t smem = 2 * n_out * x.C * sizeof(float);
+#define B200_HEAD_CASE(no) \
+  case no: k_head_bwd<no><<<blocks, threads, smem, st>>>(x, w, dlogits, dx, dw); break;
+  switch (n_out) {
+    B200_HEAD_CASE(1) B200_HEAD_CASE(2) B200_HEAD_CASE(3) B200_HEAD_CASE(4)
+    B200_HEAD_CASE(5) B200_HEAD_CASE(6) B200_HEAD_CASE(7) B200_HEAD_CASE(8)
+  }
+#undef B200_HEAD_CASE
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

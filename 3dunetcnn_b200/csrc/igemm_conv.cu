@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   const int total_iters = (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
+    {
+      const uint32_t issue = elect_one() ? 1u : 0u;
       int it = 0;
       for (int src = 0; src < 2; ++src) {
         const int nt = p.ntaps[src];
@@ -107,10 +108,10 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
               const int s = it % Cfg::STAGES;
               const uint32_t ph = (it / Cfg::STAGES) & 1;
               mbar_wait(&empty_bar[s], ph ^ 1);
-              mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BOX_BYTES);
+              mbar_expect_tx_if(issue, &full_bar[s], Cfg::A_BYTES + Cfg::B_BOX_BYTES);
               uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-              tma_load_5d(sa, &maps.a[src][pass == 1], &full_bar[s], kc * KC, cw, ch, cd, n);
-              tma_load_3d(sa + Cfg::A_BYTES, &maps.b[src][pass == 2], &full_bar[s], kc * KC, n0, tap);
+              tma_load_5d_if(issue, sa, &maps.a[src][pass == 1], &full_bar[s], kc * KC, cw, ch, cd, n);
+              tma_load_3d_if(issue, sa + Cfg::A_BYTES, &maps.b[src][pass == 2], &full_bar[s], kc * KC, n0, tap);
               ++it;
             }
           }
@@ -118,25 +119,27 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (convergent, one lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t hi_d = desc_hi(Cfg::SBO, Cfg::LAYOUT);
+      const uint32_t issue = elect_one() ? 1u : 0u;
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = smem_u32(smem);
       for (int it = 0; it < total_iters; ++it) {
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint32_t a_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES, 16);
+        const uint32_t b_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, 16);
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);
+        for (int k = 0; k < KC / 16; ++k)
+          umma_bf16_if(issue, tmem0, desc_from(a_lo + 2 * k, hi_d), desc_from(b_lo + 2 * k, hi_d), idesc,
+                       (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit_if(issue, &empty_bar[s]);
       }
-      umma_commit(tfull_bar);
+      umma_commit_if(issue, tfull_bar);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)

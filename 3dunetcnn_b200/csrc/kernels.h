@@ -80,7 +80,10 @@ struct WgradOp {
   int Cop;
   float* dw;   // fp32 [T][Cip][Cop]; accumulated with atomics, caller zero-fills
 };
-int launch_wgrad(const WgradOp& op, cudaStream_t st);
+int launch_wgrad(const WgradOp& op, cudaStream_t st);              // dispatcher: halo-resident kernel when eligible
+int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st);
+bool wgrad_halo_eligible(const WgradOp& op);
+int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st);
 
 // ---- descriptor-semantics probe (probe.cu)
 // tests: host array [ntests][5] = (layout_mode 0:SW128 1:none, start_off_bytes, sbo_bytes, lbo_bytes, base_offset);

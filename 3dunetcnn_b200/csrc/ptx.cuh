@@ -88,6 +88,33 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// predicated forms (see umma_bf16_if): convergent producer loops, one elected lane issues
+__device__ __forceinline__ void mbar_expect_tx_if(uint32_t issue, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(bytes), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_if(uint32_t issue, void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                               int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}\n"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_if(uint32_t issue, void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                               int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(issue)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -113,6 +140,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for warp-convergent issue loops: every lane executes the (uniform) address arithmetic, only the
+// lane whose `issue` flag is set (elect_one(), evaluated once) issues.  Keeping the loop convergent lets ptxas hold
+// descriptors in uniform registers instead of emitting an ELECT / R2UR loop around every UTCHMMA.
+__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
+}
+// descriptor with a pre-encoded constant part: lo word = (addr >> 4) | (lbo >> 4) << 16 ; hi word constant
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+
 // all previously issued MMAs of this thread -> arrive(1) on the mbarrier when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

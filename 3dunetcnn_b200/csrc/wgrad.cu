@@ -14,6 +14,7 @@
 // A CTA owns up to 512/BN accumulators (M-tiles) in TMEM and a contiguous range of voxel tiles (split-K); the dY tile
 // of a voxel block is loaded once and reused by all of the CTA's M-tiles.  Partial sums are reduced into the fp32
 // gradient buffer with vector atomics.  Split-precision mode: passes (a_hi,dy_hi), (a_lo,dy_hi), (a_hi,dy_lo).
+#include <cstdlib>
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
   const int pad = p.ksz >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t issue = elect_one() ? 1u : 0u;
       int ia = 0, id = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         int t = kb;
@@ -120,18 +122,18 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
             const int s = id % WG_D_STAGES;
             const uint32_t ph = (id / WG_D_STAGES) & 1;
             mbar_wait(&d_empty[s], ph ^ 1);
-            mbar_expect_tx(&d_full[s], Cfg::D_BYTES);
+            mbar_expect_tx_if(issue, &d_full[s], Cfg::D_BYTES);
             uint8_t* dst = smem_d + s * Cfg::D_STAGE;
 #pragma unroll
             for (int bx = 0; bx < Cfg::BPN; ++bx)
-              tma_load_5d(dst + bx * Cfg::LBO_B, &maps.dy[pass == 2], &d_full[s], co0 + bx * Cfg::CBN, w0, h0, d0, n);
+              tma_load_5d_if(issue, dst + bx * Cfg::LBO_B, &maps.dy[pass == 2], &d_full[s], co0 + bx * Cfg::CBN, w0, h0, d0, n);
             ++id;
           }
           for (int q = q0; q < q1; ++q) {
             const int s = ia % WG_A_STAGES;
             const uint32_t ph = (ia / WG_A_STAGES) & 1;
             mbar_wait(&a_empty[s], ph ^ 1);
-            mbar_expect_tx(&a_full[s], WG_A_BYTES);
+            mbar_expect_tx_if(issue, &a_full[s], WG_A_BYTES);
             uint8_t* dst = smem_a + s * WG_A_BYTES;
 #pragma unroll
             for (int bx = 0; bx < Cfg::BPM; ++bx) {
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
               if (u >= p.units) u = p.units - 1;  // duplicate a valid unit; its rows are never written back
               const int tap = u / p.nci, cic = u % p.nci;
               const int kd = tap / (p.ksz * p.ksz), kh = (tap / p.ksz) % p.ksz, kw = tap % p.ksz;
-              tma_load_5d(dst + bx * Cfg::LBO_A, &maps.a[pass == 1], &a_full[s], cic * CB, w0 * p.stride + kw - pad,
-                          h0 * p.stride + kh - pad, d0 * p.stride + kd - pad, n);
+              tma_load_5d_if(issue, dst + bx * Cfg::LBO_A, &maps.a[pass == 1], &a_full[s], cic * CB,
+                             w0 * p.stride + kw - pad, h0 * p.stride + kh - pad, d0 * p.stride + kd - pad, n);
             }
             ++ia;
           }
@@ -148,34 +150,36 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT_A), hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT_B);
+      const uint32_t issue = elect_one() ? 1u : 0u;
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a0 = smem_u32(smem_a), d0s = smem_u32(smem_d);
       int ia = 0, id = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         for (int pass = 0; pass < p.npass; ++pass) {
           const int sd = id % WG_D_STAGES;
           mbar_wait(&d_full[sd], (id / WG_D_STAGES) & 1);
-          const uint32_t b_addr = smem_u32(smem_d + sd * Cfg::D_STAGE);
-          const bool first = (kb == kb0) && (pass == 0);
+          const uint32_t b_lo = desc_lo(d0s + sd * Cfg::D_STAGE, Cfg::LBO_B);
+          const uint32_t first = (kb == kb0 && pass == 0) ? 1u : 0u;
           for (int qi = 0; qi < nq; ++qi) {
             const int sa = ia % WG_A_STAGES;
             mbar_wait(&a_full[sa], (ia / WG_A_STAGES) & 1);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + sa * WG_A_BYTES);
+            const uint32_t a_lo = desc_lo(a0 + sa * WG_A_BYTES, Cfg::LBO_A);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + k * 2 * Cfg::SBO_A, Cfg::LBO_A, Cfg::SBO_A, Cfg::LAYOUT_A);
-              const uint64_t db = make_smem_desc(b_addr + k * 2 * Cfg::SBO_B, Cfg::LBO_B, Cfg::SBO_B, Cfg::LAYOUT_B);
-              umma_bf16(tmem_base + qi * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
-            }
-            umma_commit(&a_empty[sa]);
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_if(issue, tmem0 + qi * BN, desc_from(a_lo + (k * 2 * Cfg::SBO_A >> 4), hi_a),
+                           desc_from(b_lo + (k * 2 * Cfg::SBO_B >> 4), hi_b), idesc, (k == 0) ? (first ^ 1u) : 1u);
+            umma_commit_if(issue, &a_empty[sa]);
             ++ia;
           }
-          umma_commit(&d_empty[sd]);
+          umma_commit_if(issue, &d_empty[sd]);
           ++id;
         }
       }
-      umma_commit(tfull);
+      umma_commit_if(issue, tfull);
     }
   } else {
     const int lane_base = (warp & 3) * 32;
@@ -230,6 +234,16 @@ static int launch_wg(const WgradMaps& maps, const WgradArgs& a, dim3 grid, cudaS
 }
 
 int launch_wgrad(const WgradOp& op, cudaStream_t st) {
+  static const bool no_halo = getenv("B200UNET_NO_HALO_WGRAD") != nullptr;
+  if (!no_halo && wgrad_halo_eligible(op)) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return launch_wgrad_halo(op, sms > 0 ? sms : 148, st);
+  }
+  return launch_wgrad_streaming(op, st);
+}
+
+int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st) {
   const Act& A = op.a;
   const Act& Y = op.dy;
   B200_REQUIRE(op.ksz == 1 || op.ksz == 3, E_UNSUPPORTED, "wgrad: kernel_size=%d unsupported", op.ksz);

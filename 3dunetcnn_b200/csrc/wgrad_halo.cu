@@ -1,0 +1,272 @@
+// Halo-resident weight gradient (3x3x3, stride 1) for sm_100a: successor of wgrad.cu's per-tap streaming kernel
+// for layers whose output plane is at least 8 x 16.
+//
+//   dW[tap][ci][co] += sum_v A[v + tap - 1][ci] * dY[v][co]
+//
+// A CTA owns up to 512/BN accumulators (128 x BN fp32 in TMEM), each one (ci-chunk kc, kd, kh) "row group" whose 128
+// rows are 128/KC swizzle atoms along M = the taps kw = 0,1,2(,+unused) of KC input channels: the atoms are the SAME
+// shared-memory halo box read at start addresses one voxel row apart (descriptor LBO = one row), so one TMA box
+// (KC, 10, 18, TD+2) of the activation per voxel tile serves all 27 taps instead of 27 shifted boxes.
+// K = voxels: one MMA contracts 16 voxels = 8(w) x 2(h): the two 8-row K groups are SBO = one halo row (A) / one
+// dense tile row (dY) apart.  Split-K over voxel tiles across CTAs; fp32 vector atomics into dW at the end.
+// Both operands are MN-major; shifted / re-strided descriptors rely on the absolute-address swizzle (probe.cu).
+#include <cstdlib>
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace b200 {
+
+struct WgHaloMaps {
+  CUtensorMap a[2];
+  CUtensorMap dy[2];
+};
+
+struct WgHaloArgs {
+  int N, D, H, W;
+  int Ci, Co, Cip, Cop;
+  int tiles_w, tiles_h, tiles_d, tiles_total;
+  int nkc;        // ci chunks
+  int gpk;        // accumulator groups per ci chunk
+  int qt;         // accumulators per CTA (<= 9)
+  int splits;
+  int npass;
+  float* dw;
+};
+
+template <int KC, int BN, int TD>
+struct WgHaloCfg {
+  static constexpr int RB = KC * 2;
+  static constexpr int HALO_TX = 180 * (TD + 2) * RB;
+  static constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;
+  static constexpr int CBN = BN < 64 ? BN : 64;
+  static constexpr int BPN = BN / CBN;
+  static constexpr int RBN = CBN * 2;
+  static constexpr int DY_BOX = 128 * TD * RBN;              // one box (CBN channels)
+  static constexpr int DY_TX = DY_BOX * BPN;
+  static constexpr int DY_BYTES = (DY_TX + 1023) / 1024 * 1024;
+  static constexpr int NH = 2, ND = 2;
+  static constexpr int SMEM_BYTES = NH * HALO_BYTES + ND * DY_BYTES + 1024 + 1024 + 1024;  // + tail slack + aux + align
+  static constexpr uint32_t LAYOUT_A = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
+  static constexpr uint32_t LAYOUT_B = CBN == 64 ? UMMA_SW128 : CBN == 32 ? UMMA_SW64 : UMMA_SW32;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <int KC, int BN, int TD>
+__global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ WgHaloMaps maps, const WgHaloArgs p) {
+  using Cfg = WgHaloCfg<KC, BN, TD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_h = smem;
+  uint8_t* smem_d = smem + Cfg::NH * Cfg::HALO_BYTES + 1024;   // 1 KB slack: the unused 4th tap atom reads 3 rows past a box
+  uint8_t* aux = smem_d + Cfg::ND * Cfg::DY_BYTES;
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* h_empty = h_full + Cfg::NH;
+  uint64_t* d_full = h_empty + Cfg::NH;
+  uint64_t* d_empty = d_full + Cfg::ND;
+  uint64_t* tfull = d_empty + Cfg::ND;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // role: blockIdx.y = (kc, group) ; blockIdx.z = co tile ; blockIdx.x = split
+  const int kc = blockIdx.y / p.gpk;
+  const int grp = blockIdx.y % p.gpk;
+  const int q0 = grp * p.qt;                       // first (kd,kh) index of this CTA
+  const int nq = min(p.qt, 9 - q0);
+  const int co0 = blockIdx.z * BN;
+  const int t0 = (int)((long long)p.tiles_total * blockIdx.x / p.splits);
+  const int t1 = (int)((long long)p.tiles_total * (blockIdx.x + 1) / p.splits);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(nq * BN)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.dy[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::NH; ++s) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 1); }
+      for (int s = 0; s < Cfg::ND; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 1); }
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    {
+      const uint32_t issue = elect_one() ? 1u : 0u;
+      uint32_t it = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        int t = tile;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int dt = t % p.tiles_d;
+        const int n = t / p.tiles_d;
+        const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD;
+        for (int pass = 0; pass < p.npass; ++pass, ++it) {
+          const uint32_t s = it % 2, ph = (it / 2) & 1;
+          mbar_wait(&h_empty[s], ph ^ 1);
+          mbar_expect_tx_if(issue, &h_full[s], Cfg::HALO_TX);
+          tma_load_5d_if(issue, smem_h + s * Cfg::HALO_BYTES, &maps.a[pass == 1], &h_full[s], kc * KC, w0 - 1, h0 - 1, d0 - 1, n);
+          mbar_wait(&d_empty[s], ph ^ 1);
+          mbar_expect_tx_if(issue, &d_full[s], Cfg::DY_TX);
+#pragma unroll
+          for (int bx = 0; bx < Cfg::BPN; ++bx)
+            tma_load_5d_if(issue, smem_d + s * Cfg::DY_BYTES + bx * Cfg::DY_BOX, &maps.dy[pass == 2], &d_full[s],
+                           co0 + bx * Cfg::CBN, w0, h0, d0, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t hi_a = desc_hi(10 * Cfg::RB, Cfg::LAYOUT_A), hi_b = desc_hi(8 * Cfg::RBN, Cfg::LAYOUT_B);
+      const uint32_t issue = elect_one() ? 1u : 0u;
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t h0s = smem_u32(smem_h), d0s = smem_u32(smem_d);
+      uint32_t it = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        for (int pass = 0; pass < p.npass; ++pass, ++it) {
+          const uint32_t s = it % 2, ph = (it / 2) & 1;
+          mbar_wait(&h_full[s], ph);
+          mbar_wait(&d_full[s], ph);
+          tc_fence_after();
+          const uint32_t h_lo = desc_lo(h0s + s * Cfg::HALO_BYTES, Cfg::RB);        // LBO = one voxel row: next kw tap
+          const uint32_t d_lo = desc_lo(d0s + s * Cfg::DY_BYTES, Cfg::DY_BOX);
+          const uint32_t first = it == 0 ? 1u : 0u;
+          for (int qi = 0; qi < nq; ++qi) {
+            const int q = q0 + qi;
+            const int kd = q / 3, kh = q % 3;
+            const uint32_t a_q = h_lo + (((kd * 18 + kh) * 10) * Cfg::RB >> 4);
+#pragma unroll
+            for (int dpl = 0; dpl < TD; ++dpl) {
+#pragma unroll
+              for (int hp = 0; hp < 8; ++hp) {
+                umma_bf16_if(issue, tmem0 + qi * BN, desc_from(a_q + (((dpl * 18 + 2 * hp) * 10) * Cfg::RB >> 4), hi_a),
+                             desc_from(d_lo + (((dpl * 16 + 2 * hp) * 8) * Cfg::RBN >> 4), hi_b), idesc,
+                             (dpl == 0 && hp == 0) ? (first ^ 1u) : 1u);
+              }
+            }
+          }
+          umma_commit_if(issue, &h_empty[s]);
+          umma_commit_if(issue, &d_empty[s]);
+        }
+      }
+      umma_commit_if(issue, tfull);
+    }
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int kw = row / KC;
+    const int ci = kc * KC + row % KC;
+    const bool row_ok = (kw < 3) && (ci < p.Ci) && (t1 > t0);
+    for (int qi = 0; qi < nq; ++qi) {
+      const int tap = (q0 + qi) * 3 + kw;
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + qi * BN + j * 16, r);
+        tmem_ld_wait();
+        const int c = co0 + j * 16;
+        if (row_ok) {
+          float* dst = p.dw + ((long long)tap * p.Cip + ci) * p.Cop + c;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (c + i + 3 < p.Cop) {
+              float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                     __uint_as_float(r[i + 3]));
+              atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+template <int KC, int BN, int TD>
+static int launch_wgh(const WgHaloMaps& maps, const WgHaloArgs& a, dim3 grid, cudaStream_t st) {
+  using Cfg = WgHaloCfg<KC, BN, TD>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  k_wgrad_halo<KC, BN, TD><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+bool wgrad_halo_eligible(const WgradOp& op) {
+  static const int max_c = getenv("B200UNET_WGHALO_MAXC") ? atoi(getenv("B200UNET_WGHALO_MAXC")) : 4096;
+  if (op.a.C > max_c) return false;
+  return op.ksz == 3 && op.stride == 1 && op.dy.W >= 8 && op.dy.H >= 16;
+}
+
+int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
+  const Act& A = op.a;
+  const Act& Y = op.dy;
+  B200_REQUIRE(wgrad_halo_eligible(op), E_UNSUPPORTED, "wgrad_halo: shape not eligible");
+  B200_REQUIRE(A.C % 8 == 0 && Y.C % 8 == 0 && A.ld % 8 == 0 && Y.ld % 8 == 0, E_UNSUPPORTED,
+               "wgrad_halo: channels must be multiples of 8");
+  B200_REQUIRE(op.Cop % 4 == 0 && op.Cop >= Y.C && op.Cip >= A.C, E_INVALID, "wgrad_halo: bad accumulator pitch");
+  B200_REQUIRE(A.N == Y.N && A.D == Y.D && A.H == Y.H && A.W == Y.W, E_INVALID, "wgrad_halo: shape mismatch");
+  const bool split = A.lo != nullptr || Y.lo != nullptr;
+  if (split) B200_REQUIRE(A.lo && Y.lo, E_INVALID, "wgrad_halo: split mode needs lo parts on both operands");
+  WgHaloArgs a;
+  memset(&a, 0, sizeof(a));
+  WgHaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int KC = A.C > 16 ? 32 : 16;
+  int BN = Y.C > 32 ? 64 : Y.C > 16 ? 32 : 16;
+  const int TD = 2;
+  const int CBN = BN < 64 ? BN : 64;
+  a.N = Y.N; a.D = Y.D; a.H = Y.H; a.W = Y.W;
+  a.Ci = A.C; a.Co = Y.C; a.Cip = op.Cip; a.Cop = op.Cop;
+  a.tiles_w = ceil_div(Y.W, 8); a.tiles_h = ceil_div(Y.H, 16); a.tiles_d = ceil_div(Y.D, TD);
+  a.tiles_total = a.N * a.tiles_d * a.tiles_h * a.tiles_w;
+  a.nkc = ceil_div(A.C, KC);
+  a.qt = 512 / BN;
+  if (a.qt > 9) a.qt = 9;
+  a.gpk = ceil_div(9, a.qt);
+  a.qt = ceil_div(9, a.gpk);
+  const int cotiles = ceil_div(Y.C, BN);
+  const int roles = a.nkc * a.gpk * cotiles;
+  int splits = num_sms / roles;
+  if (splits < 1) splits = 1;
+  if (splits > a.tiles_total) splits = a.tiles_total;
+  a.splits = splits;
+  a.npass = split ? 3 : 1;
+  a.dw = op.dw;
+  B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18, TD + 2, 1, swz_for_bytes(KC * 2)));
+  B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, TD, 1, swz_for_bytes(CBN * 2)));
+  if (split) {
+    B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18, TD + 2, 1, swz_for_bytes(KC * 2)));
+    B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, TD, 1, swz_for_bytes(CBN * 2)));
+  }
+  dim3 grid((unsigned)splits, (unsigned)(a.nkc * a.gpk), (unsigned)cotiles);
+#define B200_WGH_CASE(kc, bn) \
+  if (KC == kc && BN == bn) return launch_wgh<kc, bn, 2>(maps, a, grid, st);
+  B200_WGH_CASE(16, 16) B200_WGH_CASE(16, 32) B200_WGH_CASE(16, 64)
+  B200_WGH_CASE(32, 16) B200_WGH_CASE(32, 32) B200_WGH_CASE(32, 64)
+#undef B200_WGH_CASE
+  set_error("wgrad_halo: no kernel for KC=%d BN=%d", KC, BN);
+  return E_UNSUPPORTED;
+}
+
+}  // namespace b200

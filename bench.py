@@ -113,7 +113,6 @@ def cpu_reference_throughput(steps, warmup, budget_s=150.0, batch=1):
     Each step is a bounded sample: a crop of one 128^3 volume sized so (steps+warmup) steps fit `budget_s`."""
     from oracle import UNetConfig, make_state_dict, unet3d_forward, dice_loss
     from oracle.ref_loader import reference_available
-    torch.set_num_threads(os.cpu_count() or 1)
     cfg = UNetConfig(**MODEL_KW)
     kind = "port"
     model = None
@@ -147,14 +146,16 @@ def cpu_reference_throughput(steps, warmup, budget_s=150.0, batch=1):
     # on these small 3-D convolutions); the chosen count is reported as `cores`
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     best = None
-    for nt in sorted({ncpu, 64, 32, 16, 8}, reverse=True):
+    for nt in sorted({min(ncpu, 8), 16, 32, 64, ncpu}):      # ascending; stop as soon as more threads get slower
         if nt > ncpu:
             continue
         torch.set_num_threads(nt)
         step((32, 32, 32))
-        tt = min(step((32, 32, 32)), step((32, 32, 32)))
+        tt = step((32, 32, 32))
         if best is None or tt < best[0]:
             best = (tt, nt)
+        elif tt > 1.2 * best[0]:
+            break
     t32, nthreads = best
     torch.set_num_threads(nthreads)
     full = 128 ** 3

@@ -54,6 +54,21 @@ def main():
             out["fwd_ms"] = round(ms, 4)
             out["fwd_tflops"] = round(flop / ms / 1e9, 1)
             tot_ms["fwd"] += ms * COUNT[(ci, co, r)]
+        if what in ("epi", "all"):
+            res = L.Act.empty(n, r, r, r, co)
+            res.hi.normal_()
+            ms = timeit(lambda: L.conv3d(x, whi, wlo, 3, 1, y, cop, cip, res=res, stats=stats, stats_ld=co), reps)
+            out["res_ms"] = round(ms, 4)
+            out["res_tflops"] = round(flop / ms / 1e9, 1)
+            tot_ms.setdefault("res", 0.0)
+            tot_ms["res"] += ms * COUNT[(ci, co, r)]
+            coef = torch.rand(n, co, 4, device=DEV)
+            bst = torch.zeros(n, co, 2, dtype=torch.float64, device=DEV)
+            ms = timeit(lambda: L.conv3d(x, whi, wlo, 3, 1, y, cop, cip, mode=1, gn_x=res, coef=coef, coef_ld=co, bstats=bst), reps)
+            out["mode1_ms"] = round(ms, 4)
+            out["mode1_tflops"] = round(flop / ms / 1e9, 1)
+            tot_ms.setdefault("mode1", 0.0)
+            tot_ms["mode1"] += ms * COUNT[(ci, co, r)]
         if what in ("wgrad", "all"):
             dy = L.Act.empty(n, r, r, r, co)
             dy.hi.normal_()
