@@ -43,6 +43,7 @@ struct HaloCfg {
 struct HaloArgs {
   int tiles_total;   // N * tiles_d * tiles_h * tiles_w * ntiles
   int ntiles;        // output-channel tiles
+  int hsplit;        // the halo box is loaded as (TD+2) * hsplit TMA boxes of (KC, 10, 18/hsplit, 1): more boxes in flight
 };
 
 template <int KC, int BN, int TD>
@@ -112,8 +113,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
               const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
               mbar_wait(&halo_empty[s], ph ^ 1);
               mbar_expect_tx_if(issue, &halo_full[s], Cfg::HALO_TX);
-              tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES, &maps.a[src][pass == 1], &halo_full[s], kc * KC,
-                             w0 - 1, h0 - 1, d0 - 1, n);
+              const int hrows = 18 / hp.hsplit;
+              for (int dp = 0; dp < TD + 2; ++dp)
+                for (int hq = 0; hq < hp.hsplit; ++hq)
+                  tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES + ((dp * 18 + hq * hrows) * 10) * Cfg::RB,
+                                 &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1, h0 - 1 + hq * hrows, d0 - 1 + dp, n);
               ++hi;
             }
             for (int tap = 0; tap < ntap; ++tap) {
@@ -300,14 +304,20 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
   a.tw = 8; a.th = 16; a.td = TD;
   a.tiles_w = ceil_div(out.W, 8); a.tiles_h = ceil_div(out.H, 16); a.tiles_d = ceil_div(out.D, TD);
   const Swz swz = swz_for_bytes(KC * 2);
+  // sub-boxes must start on 128-byte boundaries: rows * RB % 128 == 0
+  int hsplit = KC == 32 ? 2 : 1;
+  if (const char* e = getenv("B200UNET_HALO_HSPLIT")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 3 || v == 6) && ((18 / v) * 10 * KC * 2) % 128 == 0) hsplit = v;
+  }
   for (int s = 0; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = 1;
     a.kchunks[s] = ceil_div(c.x.C, KC);
-    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18, TD + 2, 1, swz));
+    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz));
     B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     if (split) {
-      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18, TD + 2, 1, swz));
+      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz));
       B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     }
   }
@@ -329,6 +339,7 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
   }
   HaloArgs h;
   h.ntiles = ntiles;
+  h.hsplit = hsplit;
   h.tiles_total = (int)tiles_for(TD);
   const int grid = h.tiles_total < num_sms ? h.tiles_total : num_sms;
 #define B200_HALO_CASE(kc, bn, td) \

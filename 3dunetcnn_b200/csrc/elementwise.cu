@@ -681,6 +681,53 @@ int launch_unpack_wgrad(const float* g, int Co, int Ci, int Cop, int Cip, int T,
   return OK;
 }
 
+// ---- batched forms: one launch packs / unpacks every convolution of the network (blockIdx.y = job)
+__global__ void k_pack_all(PtrTable params, const PackJob* __restrict__ jobs, uint8_t* __restrict__ ws, int split) {
+  const PackJob j = jobs[blockIdx.y];
+  const float* __restrict__ w = reinterpret_cast<const float*>(params.p[j.pidx]);
+  bf16* hi = reinterpret_cast<bf16*>(ws + j.off_hi);
+  bf16* lo = split ? reinterpret_cast<bf16*>(ws + j.off_lo) : nullptr;
+  const long long total = (long long)j.T * j.Cop * j.Cip;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (j.mode == 0) {
+      const int ci = (int)(i % j.Cip); const int co = (int)((i / j.Cip) % j.Cop); const int t = (int)(i / ((long long)j.Cip * j.Cop));
+      if (ci < j.Ci && co < j.Co) v = w[((long long)co * j.Ci + ci) * j.T + t];
+    } else {
+      const int co = (int)(i % j.Cop); const int ci = (int)((i / j.Cop) % j.Cip); const int t = (int)(i / ((long long)j.Cip * j.Cop));
+      if (ci < j.Ci && co < j.Co) v = w[((long long)co * j.Ci + ci) * j.T + (j.T - 1 - t)];
+    }
+    bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+int launch_pack_all(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st) {
+  if (njobs == 0) return OK;
+  k_pack_all<<<dim3(48, njobs), 256, 0, st>>>(params, jobs_dev, ws, split ? 1 : 0);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+__global__ void k_unpack_all(PtrTable grads, const PackJob* __restrict__ jobs, const uint8_t* __restrict__ ws) {
+  const PackJob j = jobs[blockIdx.y];
+  float* __restrict__ out = const_cast<float*>(reinterpret_cast<const float*>(grads.p[j.pidx]));
+  const float* __restrict__ g = reinterpret_cast<const float*>(ws + j.off_hi);   // fp32 accumulator [T][Cip][Cop]
+  const long long total = (long long)j.T * j.Co * j.Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % j.T); const int ci = (int)((i / j.T) % j.Ci); const int co = (int)(i / ((long long)j.T * j.Ci));
+    out[i] = g[((long long)t * j.Cip + ci) * j.Cop + co];
+  }
+}
+
+int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st) {
+  if (njobs == 0) return OK;
+  k_unpack_all<<<dim3(48, njobs), 256, 0, st>>>(grads, jobs_dev, ws);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
 // ------------------------------------------------------------------------------------------------ zero insertion (x2 dilation)
 // z[2d+od][2h+oh][2w+ow] = x[d][h][w], zeros elsewhere; z dims given by the view (>= 2*x dims - 1 + offset).
 __global__ void k_zero_insert(Act x, Act z, int od, int oh, int ow) {

@@ -24,6 +24,16 @@ int launch_pack_weights(const float* w, int Co, int Ci, int Cop, int Cip, int T,
                         cudaStream_t st);
 int launch_unpack_wgrad(const float* g, int Co, int Ci, int Cop, int Cip, int T, int mode, float* out,
                         cudaStream_t st);
+// batched weight packing / gradient unpacking (one launch for the whole network)
+struct PtrTable { const void* p[256]; };
+struct PackJob {
+  int pidx;                 // index into the parameter / gradient pointer table
+  int Co, Ci, Cop, Cip, T;
+  int mode;                 // 0 forward [T][Cop][Cip], 1 data-gradient [T][Cip][Cop] flipped
+  long long off_hi, off_lo; // workspace byte offsets (unpack: off_hi = fp32 accumulator)
+};
+int launch_pack_all(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st);
+int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st);
 int launch_zero_insert(const Act& x, const Act& z, int od, int oh, int ow, cudaStream_t st);
 int launch_ncdhw_to_act(const float* x, int C, const Act& out, cudaStream_t st);
 int launch_act_to_ncdhw(const Act& in, int C, float* y, cudaStream_t st);

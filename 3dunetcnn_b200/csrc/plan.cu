@@ -109,6 +109,9 @@ struct b200unet_plan {
   size_t bz_off = 0, bz_bytes = 0;        // zeroed at the start of every backward (bstats + dw accumulators)
   int last_launches = 0;
   int head_param = -1;
+  std::vector<PackJob> pack_jobs, unpack_jobs;   // batched weight (un)packing tables (host copies)
+  size_t jobs_off = 0;                           // device copy: pack jobs then unpack jobs
+  const void* jobs_uploaded_for = nullptr;       // workspace base the table was last uploaded into
   Prof* prof = nullptr;
   double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
@@ -286,16 +289,7 @@ static inline void prof_mark(RunCtx& cx, int cat, bool end) {
 
 // ---- forward op emitters
 static void emit_pack(Plan& P, int ci) {
-  P.fwd.push_back([&P, ci](RunCtx& cx) -> int {
-    const ConvLayer& c = P.convs[ci];
-    const float* w = cx.params[c.pw];
-    LAUNCHED(cx, CAT_PACK, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 0, reinterpret_cast<bf16*>(cx.ws + c.wf_hi),
-                                     P.split ? reinterpret_cast<bf16*>(cx.ws + c.wf_lo) : nullptr, cx.st));
-    if (c.need_dgrad)
-      LAUNCHED(cx, CAT_PACK, launch_pack_weights(w, c.Co, c.Ci, c.Cop, c.Cip, c.T, 1, reinterpret_cast<bf16*>(cx.ws + c.wd_hi),
-                                       P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr, cx.st));
-    return OK;
-  });
+  (void)P; (void)ci;   // packing is batched: see the k_pack_all launch at the head of the forward schedule
 }
 
 static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
@@ -501,6 +495,20 @@ static int build(Plan& P) {
   need_stats(P, b_in);
   P.fwd.push_back([&P, b_in](RunCtx& cx) -> int {
     B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.stats_off, 0, P.stats_bytes, cx.st));
+    if (P.jobs_uploaded_for != cx.ws) {     // (re)upload the constant job tables into this workspace
+      std::vector<PackJob> all(P.pack_jobs);
+      all.insert(all.end(), P.unpack_jobs.begin(), P.unpack_jobs.end());
+      B200_CHECK_CUDA(cudaMemcpyAsync(cx.ws + P.jobs_off, all.data(), sizeof(PackJob) * all.size(), cudaMemcpyHostToDevice, cx.st));
+      B200_CHECK_CUDA(cudaStreamSynchronize(cx.st));   // `all` is a temporary; happens once per workspace
+      P.jobs_uploaded_for = cx.ws;
+    }
+    {
+      PtrTable tbl;
+      memset(&tbl, 0, sizeof(tbl));
+      for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.params[i];
+      LAUNCHED(cx, CAT_PACK, launch_pack_all(tbl, reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off), (int)P.pack_jobs.size(),
+                                             cx.ws, P.split, cx.st));
+    }
     TRef t = full(P, b_in);
     LAUNCHED(cx, CAT_RESAMPLE, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), stats_ptr(P, cx, t), P.bufs[b_in].C, cx.st));
     return OK;
@@ -653,21 +661,33 @@ static int build(Plan& P) {
       g = gS;
     }
   }
-  // weight gradients: accumulator -> torch layout
-  for (size_t ci = 0; ci < P.convs.size(); ++ci) {
-    P.bwd.push_back([&P, ci](RunCtx& cx) -> int {
-      const ConvLayer& c = P.convs[ci];
-      LAUNCHED(cx, CAT_PACK, launch_unpack_wgrad(reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw), c.Co, c.Ci, c.Cop, c.Cip, c.T, 0,
-                                       cx.grads[c.pw], cx.st));
-      return OK;
-    });
-  }
+  // weight gradients: accumulator -> torch layout (one batched launch)
+  P.bwd.push_back([&P](RunCtx& cx) -> int {
+    PtrTable tbl;
+    memset(&tbl, 0, sizeof(tbl));
+    for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.grads[i];
+    const PackJob* jobs = reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off) + P.pack_jobs.size();
+    LAUNCHED(cx, CAT_PACK, launch_unpack_all(tbl, jobs, (int)P.unpack_jobs.size(), cx.ws, cx.st));
+    return OK;
+  });
   // arenas that are bulk-zeroed
+  B200_REQUIRE(P.params.size() <= 256, E_UNSUPPORTED, "plan: more than 256 parameter tensors");
   P.drop_off = P.alloc(sizeof(float) * N * d.base_width);
   P.stats_off = P.alloc(P.stats_bytes);
   P.bz_off = P.alloc(P.bz_bytes);
   for (size_t i = 0; i < P.convs.size(); ++i)
     B200_REQUIRE(P.convs[i].pw >= 0, E_INVALID, "plan: internal: conv %d has no parameter", (int)i);
+  for (const ConvLayer& c : P.convs) {
+    PackJob j;
+    j.pidx = c.pw; j.Co = c.Co; j.Ci = c.Ci; j.Cop = c.Cop; j.Cip = c.Cip; j.T = c.T;
+    j.mode = 0; j.off_hi = (long long)c.wf_hi; j.off_lo = (long long)c.wf_lo;
+    P.pack_jobs.push_back(j);
+    if (c.need_dgrad) { j.mode = 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo; P.pack_jobs.push_back(j); }
+    PackJob u = j;
+    u.mode = 0; u.off_hi = (long long)(P.bz_off + c.dw); u.off_lo = 0;
+    P.unpack_jobs.push_back(u);
+  }
+  P.jobs_off = P.alloc(sizeof(PackJob) * (P.pack_jobs.size() + P.unpack_jobs.size()));
   return OK;
 }
 

@@ -31,6 +31,7 @@ struct WgHaloArgs {
   int qt;         // accumulators per CTA (<= 9)
   int splits;
   int npass;
+  int hsplit;     // halo box loaded as (TD+2)*hsplit TMA boxes, dY tile as TD boxes (more requests in flight)
   float* dw;
 };
 
@@ -114,13 +115,18 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
           const uint32_t s = it % 2, ph = (it / 2) & 1;
           mbar_wait(&h_empty[s], ph ^ 1);
           mbar_expect_tx_if(issue, &h_full[s], Cfg::HALO_TX);
-          tma_load_5d_if(issue, smem_h + s * Cfg::HALO_BYTES, &maps.a[pass == 1], &h_full[s], kc * KC, w0 - 1, h0 - 1, d0 - 1, n);
+          const int hrows = 18 / p.hsplit;
+          for (int dp = 0; dp < TD + 2; ++dp)
+            for (int hq = 0; hq < p.hsplit; ++hq)
+              tma_load_5d_if(issue, smem_h + s * Cfg::HALO_BYTES + ((dp * 18 + hq * hrows) * 10) * Cfg::RB, &maps.a[pass == 1],
+                             &h_full[s], kc * KC, w0 - 1, h0 - 1 + hq * hrows, d0 - 1 + dp, n);
           mbar_wait(&d_empty[s], ph ^ 1);
           mbar_expect_tx_if(issue, &d_full[s], Cfg::DY_TX);
 #pragma unroll
           for (int bx = 0; bx < Cfg::BPN; ++bx)
-            tma_load_5d_if(issue, smem_d + s * Cfg::DY_BYTES + bx * Cfg::DY_BOX, &maps.dy[pass == 2], &d_full[s],
-                           co0 + bx * Cfg::CBN, w0, h0, d0, n);
+            for (int dp = 0; dp < TD; ++dp)
+              tma_load_5d_if(issue, smem_d + s * Cfg::DY_BYTES + bx * Cfg::DY_BOX + dp * 128 * Cfg::RBN, &maps.dy[pass == 2],
+                             &d_full[s], co0 + bx * Cfg::CBN, w0, h0, d0 + dp, n);
         }
       }
     }
@@ -213,7 +219,7 @@ static int launch_wgh(const WgHaloMaps& maps, const WgHaloArgs& a, dim3 grid, cu
 }
 
 bool wgrad_halo_eligible(const WgradOp& op) {
-  static const int max_c = getenv("B200UNET_WGHALO_MAXC") ? atoi(getenv("B200UNET_WGHALO_MAXC")) : 4096;
+  static const int max_c = getenv("B200UNET_WGHALO_MAXC") ? atoi(getenv("B200UNET_WGHALO_MAXC")) : 64;
   if (op.a.C > max_c) return false;
   return op.ksz == 3 && op.stride == 1 && op.dy.W >= 8 && op.dy.H >= 16;
 }
@@ -253,11 +259,17 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
   a.splits = splits;
   a.npass = split ? 3 : 1;
   a.dw = op.dw;
-  B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18, TD + 2, 1, swz_for_bytes(KC * 2)));
-  B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, TD, 1, swz_for_bytes(CBN * 2)));
+  int hsplit = KC == 32 ? 2 : 1;
+  if (const char* e = getenv("B200UNET_HALO_HSPLIT")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 3 || v == 6) && ((18 / v) * 10 * KC * 2) % 128 == 0) hsplit = v;
+  }
+  a.hsplit = hsplit;
+  B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2)));
+  B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2)));
   if (split) {
-    B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18, TD + 2, 1, swz_for_bytes(KC * 2)));
-    B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, TD, 1, swz_for_bytes(CBN * 2)));
+    B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2)));
+    B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2)));
   }
   dim3 grid((unsigned)splits, (unsigned)(a.nkc * a.gpk), (unsigned)cotiles);
 #define B200_WGH_CASE(kc, bn) \
