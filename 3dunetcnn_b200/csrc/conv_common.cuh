@@ -87,67 +87,111 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 }
 
 
-// Fused epilogue for one 128-row accumulator tile living at TMEM address `tacc` (lane quadrant already applied by
-// the caller through `lane_base`): per 16-column chunk  tcgen05.ld -> (+residual)(*scale) | GN/ReLU backward ->
-// hi/lo store -> per-channel partial sums into s_stats.  `vox` = linear NDHW index of this thread's row.
+// L2 prefetch of the epilogue's side input (residual in mode 0, the norm's raw input in mode 1) for one output row.
+// Issued at tile start, long before the accumulator is ready: the DRAM latency overlaps the MMAs, the later loads hit L2.
+__device__ __forceinline__ void conv_epilogue_prefetch(const ConvArgs& p, int n0, int ncols, long long vox, bool valid) {
+  const bf16* hi = p.mode == 0 ? p.res_hi : p.x_hi;
+  if (!hi || !valid) return;
+  const bf16* lo = p.mode == 0 ? p.res_lo : p.x_lo;
+  const int ld = p.mode == 0 ? p.ldr : p.ldx;
+  int c1 = n0 + ncols;
+  if (c1 > p.Cout) c1 = p.Cout;
+  for (int c = n0; c < c1; c += 64) {   // one 128-byte line per 64 channels
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(hi + vox * ld + c));
+    if (lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(lo + vox * ld + c));
+  }
+}
+
+// Fused epilogue for one 128-row accumulator tile living at TMEM address `tacc` (lane quadrant applied through
+// `lane_base`).  Columns are processed in groups of <= 64: the group's side input (residual / norm input) is loaded
+// into registers up front (one latency per group instead of one per 16-column chunk), then per 16-column chunk:
+// tcgen05.ld -> (+residual)(*scale) | GN/ReLU backward -> hi/lo store -> per-channel partial sums into s_stats.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t tacc, int lane_base, int lane, int n,
                                                    int n0, long long vox, bool valid, float* s_stats,
                                                    const float4* s_coef, bool want_stats) {
+  constexpr int G = BN < 64 ? BN : 64;
+  const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
+  const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
+  const int side_ld = p.mode == 0 ? p.ldr : p.ldx;
 #pragma unroll 1
-  for (int j = 0; j < BN / 16; ++j) {
-    const int c0 = n0 + j * 16;
-    if (c0 >= p.Cout) break;
-    uint32_t r[16];
-    tmem_ld16(tacc + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
-    tmem_ld_wait();
-    float v[16], q[16];
+  for (int g0 = 0; g0 < BN; g0 += G) {
+    if (n0 + g0 >= p.Cout) break;
+    uint4 ph[G / 8], pl[G / 8];
+    if (side_hi && valid) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int cc = c0 + hf * 8;
-      float* vv = v + hf * 8;
-      float* qq = q + hf * 8;
-      if (cc < p.Cout && valid) {
-        if (p.mode == 0) {
-          if (p.res_hi) {
-            float rr[8];
-            epi_load8(p.res_hi, p.res_lo, vox * p.ldr + cc, rr);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] += rr[i];
-          }
-          if (p.scale) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) qq[i] = vv[i] * vv[i];
-        } else {
-          float xx[8];
-          epi_load8(p.x_hi, p.x_lo, vox * p.ldx + cc, xx);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 k = s_coef[j * 16 + hf * 8 + i];
-            const float z = fmaf(k.x, xx[i], k.y);
-            const float dz = z > 0.f ? vv[i] : vv[i] * p.slope;
-            vv[i] = dz;
-            qq[i] = dz * (xx[i] - k.z) * k.w;
-          }
+      for (int i = 0; i < G / 8; ++i) {
+        const int cc = n0 + g0 + i * 8;
+        if (cc < p.Cout) {
+          ph[i] = *reinterpret_cast<const uint4*>(side_hi + vox * side_ld + cc);
+          if (side_lo) pl[i] = *reinterpret_cast<const uint4*>(side_lo + vox * side_ld + cc);
         }
-        epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { vv[i] = 0.f; qq[i] = 0.f; }
       }
     }
-    if (want_stats) {
-      const float s1 = warp_colsum16(v, lane);
-      const float s2 = warp_colsum16(q, lane);
-      if ((lane & 1) == 0) {
-        const int col = j * 16 + ((lane >> 1) & 15);
-        atomicAdd(&s_stats[col * 2 + 0], s1);
-        atomicAdd(&s_stats[col * 2 + 1], s2);
+#pragma unroll
+    for (int jj = 0; jj < G / 16; ++jj) {
+      const int j = g0 / 16 + jj;
+      const int c0 = n0 + j * 16;
+      if (c0 < p.Cout) {
+        uint32_t r[16];
+        tmem_ld16(tacc + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
+        tmem_ld_wait();
+        float v[16], q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int cc = c0 + hf * 8;
+          float* vv = v + hf * 8;
+          float* qq = q + hf * 8;
+          if (cc < p.Cout && valid) {
+            float sv[8];
+            if (side_hi) {
+              const uint4 a = ph[jj * 2 + hf];
+              sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
+              sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
+              if (side_lo) {
+                const uint4 b = pl[jj * 2 + hf];
+                sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
+                sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);
+              }
+            }
+            if (p.mode == 0) {
+              if (side_hi) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += sv[i];
+              }
+              if (p.scale) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) qq[i] = vv[i] * vv[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 k = s_coef[j * 16 + hf * 8 + i];
+                const float z = fmaf(k.x, sv[i], k.y);
+                const float dz = z > 0.f ? vv[i] : vv[i] * p.slope;
+                vv[i] = dz;
+                qq[i] = dz * (sv[i] - k.z) * k.w;
+              }
+            }
+            epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { vv[i] = 0.f; qq[i] = 0.f; }
+          }
+        }
+        if (want_stats) {
+          const float s1 = warp_colsum16(v, lane);
+          const float s2 = warp_colsum16(q, lane);
+          if ((lane & 1) == 0) {
+            const int col = j * 16 + ((lane >> 1) & 15);
+            atomicAdd(&s_stats[col * 2 + 0], s1);
+            atomicAdd(&s_stats[col * 2 + 1], s2);
+          }
+        }
       }
     }
   }

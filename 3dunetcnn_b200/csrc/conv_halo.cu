@@ -183,12 +183,44 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Loop order: 16-column chunk outer, the tile's TD planes inner, so the per-channel statistics are accumulated
+    // in registers over planes (BN >= 64: one butterfly reduction per chunk per tile) or over planes AND tiles
+    // (BN <= 32: "running" sums, reduced only when the sample / channel tile changes and at the end).  The
+    // butterflies were the bottleneck of the narrow layers (ncu: profiles/r01_halo_epilogue.txt).
+    constexpr bool RUN = (BN <= 32);
+    constexpr int NCH = BN / 16;
+    constexpr int NACCUM = RUN ? BN : 16;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const int e = threadIdx.x - 64;
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
+    const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
+    const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
+    const int side_ld = p.mode == 0 ? p.ldr : p.ldx;
+    double* stat_dst = (p.mode == 0) ? p.stats : p.bstats;
+    const int stat_ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
+    float rs[NACCUM], rq[NACCUM];
+#pragma unroll
+    for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     uint32_t ti = 0;
-    int coef_n = -1, coef_n0 = -1;
+    int cur_n = -1, cur_n0 = -1;
+
+    // s_stats (already holding every warp's partial sums) -> global fp64 atomics, then re-zero
+    auto flush_smem = [&](int fn, int fn0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = e; c < BN; c += 128) {
+        if (fn0 + c < p.Cout) {
+          atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
+          atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
+        }
+        s_stats[c * 2 + 0] = 0.f;
+        s_stats[c * 2 + 1] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       int t = tile;
       const int nt = t % hp.ntiles; t /= hp.ntiles;
@@ -197,41 +229,150 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       const int dt = t % p.tiles_d;
       const int n = t / p.tiles_d;
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
-      // per-tile shared state: zero the statistics, (re)load the GN coefficients when (n, n0) changes
-      for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
-      if (p.mode == 1 && (n != coef_n || n0 != coef_n0)) {
-        for (int c = e; c < BN; c += 128)
-          s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        coef_n = n; coef_n0 = n0;
+      if (n != cur_n || n0 != cur_n0) {
+        if (RUN && want_stats && cur_n >= 0) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            float v16[16], q16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v16[i] = rs[(RUN ? j * 16 : 0) + i]; q16[i] = rq[(RUN ? j * 16 : 0) + i]; }
+            const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
+            if ((lane & 1) == 0) {
+              const int col = j * 16 + ((lane >> 1) & 15);
+              atomicAdd(&s_stats[col * 2 + 0], s1);
+              atomicAdd(&s_stats[col * 2 + 1], s2);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+          flush_smem(cur_n, cur_n0);
+        }
+        if (p.mode == 1) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // nobody still reads the old coefficients
+          for (int c = e; c < BN; c += 128)
+            s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        cur_n = n; cur_n0 = n0;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int w = w0 + (row & 7), h = h0 + (row >> 3);
+      const bool valid_wh = (w < p.Wo) && (h < p.Ho);
+      const long long vox0 = (((long long)n * p.Do + d0) * p.Ho + h) * p.Wo + w;   // plane dpl: + dpl * Ho * Wo
+      const long long plane = (long long)p.Ho * p.Wo;
+#pragma unroll
+      for (int dpl = 0; dpl < TD; ++dpl)     // side-input rows of this tile -> L2 while the MMAs are still running
+        conv_epilogue_prefetch(p, n0, BN, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
       const uint32_t as = ti % Cfg::NACC;
       mbar_wait(&acc_full[as], (ti / Cfg::NACC) & 1);
       tc_fence_after();
-      const int w = w0 + (row & 7), h = h0 + (row >> 3);
-#pragma unroll 1
-      for (int dpl = 0; dpl < TD; ++dpl) {
-        const int d = d0 + dpl;
-        const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
-        const long long vox = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-        conv_epilogue_tile<BN>(p, tmem_base + (as * TD + dpl) * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef,
-                               want_stats);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int c0 = n0 + j * 16;
+        if (c0 < p.Cout) {
+          // side input (residual / norm input) of this chunk for all planes: one latency for TD planes
+          uint4 sh[TD][2], sl[TD][2];
+          if (side_hi) {
+#pragma unroll
+            for (int dpl = 0; dpl < TD; ++dpl) {
+              if (valid_wh && (d0 + dpl < p.Do)) {
+                const long long off = (vox0 + dpl * plane) * side_ld + c0;
+                sh[dpl][0] = *reinterpret_cast<const uint4*>(side_hi + off);
+                if (c0 + 8 < p.Cout) sh[dpl][1] = *reinterpret_cast<const uint4*>(side_hi + off + 8);
+                if (side_lo) {
+                  sl[dpl][0] = *reinterpret_cast<const uint4*>(side_lo + off);
+                  if (c0 + 8 < p.Cout) sl[dpl][1] = *reinterpret_cast<const uint4*>(side_lo + off + 8);
+                }
+              }
+            }
+          }
+          float* as_ = rs + (RUN ? j * 16 : 0);
+          float* aq_ = rq + (RUN ? j * 16 : 0);
+#pragma unroll
+          for (int dpl = 0; dpl < TD; ++dpl) {
+            const bool valid = valid_wh && (d0 + dpl < p.Do);
+            const long long vox = vox0 + dpl * plane;
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (as * TD + dpl) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int cc = c0 + hf * 8;
+              if (cc < p.Cout && valid) {
+                float vv[8], sv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[hf * 8 + i]);
+                if (side_hi) {
+                  const uint4 a = sh[dpl][hf];
+                  sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
+                  sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
+                  if (side_lo) {
+                    const uint4 b = sl[dpl][hf];
+                    sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
+                    sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);
+                  }
+                }
+                if (p.mode == 0) {
+                  if (side_hi) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vv[i] += sv[i];
+                  }
+                  if (p.scale) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { as_[hf * 8 + i] += vv[i]; aq_[hf * 8 + i] = fmaf(vv[i], vv[i], aq_[hf * 8 + i]); }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 k = s_coef[j * 16 + hf * 8 + i];
+                    const float z = fmaf(k.x, sv[i], k.y);
+                    const float dz = z > 0.f ? vv[i] : vv[i] * p.slope;
+                    vv[i] = dz;
+                    as_[hf * 8 + i] += dz;
+                    aq_[hf * 8 + i] = fmaf(dz, (sv[i] - k.z) * k.w, aq_[hf * 8 + i]);
+                  }
+                }
+                epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
+              }
+            }
+          }
+          if constexpr (!RUN) {
+            if (want_stats) {
+              float v16[16], q16[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v16[i] = rs[i]; q16[i] = rq[i]; }
+              const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
+              if ((lane & 1) == 0) {
+                const int col = j * 16 + ((lane >> 1) & 15);
+                atomicAdd(&s_stats[col * 2 + 0], s1);
+                atomicAdd(&s_stats[col * 2 + 1], s2);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);      // accumulator set drained: MMA may overwrite it
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // all partial sums are in s_stats
-      if (want_stats) {
-        double* dst = (p.mode == 0) ? p.stats : p.bstats;
-        const int ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
-        for (int c = e; c < BN; c += 128) {
-          if (n0 + c < p.Cout) {
-            atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
-            atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
-          }
+      if (!RUN && want_stats) flush_smem(n, n0);
+    }
+    if (RUN && want_stats && cur_n >= 0) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        float v16[16], q16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v16[i] = rs[(RUN ? j * 16 : 0) + i]; q16[i] = rq[(RUN ? j * 16 : 0) + i]; }
+        const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
+        if ((lane & 1) == 0) {
+          const int col = j * 16 + ((lane >> 1) & 15);
+          atomicAdd(&s_stats[col * 2 + 0], s1);
+          atomicAdd(&s_stats[col * 2 + 1], s2);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // flushed before the next tile zeroes s_stats
+      flush_smem(cur_n, cur_n0);
     }
   }
   __syncthreads();

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     const int w = w0 + wl, h = h0 + hl, d = d0 + dl;
     const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
     const long long vox = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+    conv_epilogue_prefetch(p, n0, BN, vox, valid);
     asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
