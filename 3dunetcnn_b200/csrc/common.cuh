@@ -46,11 +46,12 @@ struct Act {
   bf16* lo;
   int N, D, H, W, C;  // logical extent; C = channels visible through this view
   int ld;             // channel pitch of the underlying buffer in elements (>= C)
+  int vD, vH, vW;     // optional "visible" spatial extents (0 = D/H/W): voxels beyond them read as zero through TMA
   __host__ __device__ long long voxels() const { return (long long)N * D * H * W; }
 };
 
 static inline Act make_act(bf16* hi, bf16* lo, int N, int D, int H, int W, int C, int ld) {
-  Act a; a.hi = hi; a.lo = lo; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C; a.ld = ld; return a;
+  Act a; a.hi = hi; a.lo = lo; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C; a.ld = ld; a.vD = a.vH = a.vW = 0; return a;
 }
 static inline Act slice_c(const Act& a, int c0, int c) {
   Act r = a; r.hi = a.hi + c0; r.lo = a.lo ? a.lo + c0 : nullptr; r.C = c; return r;

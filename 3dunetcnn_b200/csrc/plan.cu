@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <cstdio>
 
 #include "kernels.h"
 #include "../../include/b200unet.h"
@@ -47,6 +48,7 @@ struct RunCtx {
   cudaStream_t st;
   int launches;
   struct Prof* prof;
+  const char* label;   // name of the op being launched (profiling only)
 };
 
 enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_NORM, CAT_RESAMPLE, CAT_HEAD, CAT_PACK, CAT_OTHER, CAT_COUNT };
@@ -54,6 +56,7 @@ enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_NORM, CAT_RESAM
 struct Prof {
   std::vector<cudaEvent_t> ev;    // 2 per launch
   std::vector<int> cat;
+  std::vector<std::string> label;
   size_t used = 0;                // launches recorded
   bool overflow = false;
 };
@@ -65,6 +68,7 @@ struct ConvLayer {
   size_t wd_hi, wd_lo;     // packed data-grad weights [T][Cip][Cop]
   size_t dw;               // fp32 accumulator         [T][Cip][Cop]
   bool need_dgrad;
+  std::string name;        // state-dict key (profiling labels)
 };
 
 struct NormLayer {
@@ -72,6 +76,7 @@ struct NormLayer {
   int C, Cld, G;
   long long S;
   size_t coef, coef2, bstats;
+  std::string name;
 };
 
 struct BlockRec {
@@ -91,6 +96,10 @@ struct StageRec {  // decoder up-sampling stage
 };
 
 typedef std::function<int(RunCtx&)> OpFn;
+
+static inline void push_op(std::vector<OpFn>& list, const std::string& label, OpFn fn) {
+  list.push_back([label, fn](RunCtx& cx) -> int { cx.label = label.c_str(); return fn(cx); });
+}
 
 }  // namespace b200
 
@@ -245,6 +254,7 @@ static double* stats_ptr(const Plan& P, const RunCtx& cx, TRef t) {
 static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, int stride, bool need_dgrad) {
   ConvLayer c;
   c.pw = P.find_param(key);
+  c.name = key;
   c.Co = Co; c.Ci = Ci; c.Cop = round_up(Co, 8); c.Cip = round_up(Ci, 8);
   c.ksz = ksz; c.stride = stride; c.T = ksz * ksz * ksz;
   c.need_dgrad = need_dgrad;
@@ -261,6 +271,7 @@ static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, in
 
 static int new_norm(Plan& P, const std::string& prefix, int C, int Cld, long long S) {
   NormLayer n;
+  n.name = prefix;
   n.pg = P.find_param(prefix + ".weight");
   n.pb = P.find_param(prefix + ".bias");
   n.C = C; n.Cld = Cld; n.G = groups_for(C, P.d.norm_groups); n.S = S;
@@ -278,6 +289,7 @@ static inline void prof_mark(RunCtx& cx, int cat, bool end) {
   if (!end) {
     if ((p->used + 1) * 2 > p->ev.size()) { p->overflow = true; return; }
     p->cat[p->used] = cat;
+    p->label[p->used] = cx.label ? cx.label : "";
     cudaEventRecord(p->ev[p->used * 2], cx.st);
   } else {
     if (p->overflow) return;
@@ -287,13 +299,18 @@ static inline void prof_mark(RunCtx& cx, int cat, bool end) {
 }
 #define LAUNCHED(cx, cat, expr) do { prof_mark(cx, cat, false); B200_TRY(expr); prof_mark(cx, cat, true); (cx).launches++; } while (0)
 
+static std::string shape_of(const Plan& P, TRef t) {
+  const Buf& b = P.bufs[t.buf];
+  return std::to_string(t.c) + "ch@" + std::to_string(b.D) + "x" + std::to_string(b.H) + "x" + std::to_string(b.W);
+}
+
 // ---- forward op emitters
 static void emit_pack(Plan& P, int ci) {
   (void)P; (void)ci;   // packing is batched: see the k_pack_all launch at the head of the forward schedule
 }
 
 static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
-  P.fwd.push_back([&P, ni, x, y](RunCtx& cx) -> int {
+  push_op(P.fwd, "gn_apply " + P.norms[ni].name + " " + shape_of(P, x), [&P, ni, x, y](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
     LAUNCHED(cx, CAT_NORM, launch_gn_finalize(stats_ptr(P, cx, x), cx.params[n.pg], cx.params[n.pb], P.d.batch, n.C, n.Cld, n.G,
                                     n.S, 1e-5f, reinterpret_cast<float*>(cx.ws + n.coef), cx.st));
@@ -313,7 +330,8 @@ static double conv_macs(const Plan& P, int ci, TRef out_like) {
 static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, TRef out, bool stats, bool scale) {
   if (stats) need_stats(P, out.buf);
   P.macs[CAT_CONV_FWD] += conv_macs(P, ci, out) + (ci2 >= 0 ? conv_macs(P, ci2, out) : 0.0);
-  P.fwd.push_back([&P, ci, a, ci2, a2, res, out, stats, scale](RunCtx& cx) -> int {
+  push_op(P.fwd, "conv_fwd " + P.convs[ci].name + " " + shape_of(P, a) + "->" + shape_of(P, out) + (ci2 >= 0 ? " +sample" : "") + (res.valid() ? " +res" : ""),
+          [&P, ci, a, ci2, a2, res, out, stats, scale](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
     memset(&op, 0, sizeof(op));
@@ -344,7 +362,7 @@ static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, T
 // ---- backward op emitters
 static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
   P.macs[CAT_CONV_WGRAD] += conv_macs(P, ci, dy);
-  P.bwd.push_back([&P, ci, a, dy](RunCtx& cx) -> int {
+  push_op(P.bwd, "wgrad " + P.convs[ci].name + " " + shape_of(P, a) + " x " + shape_of(P, dy), [&P, ci, a, dy](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     WgradOp op;
     op.a = act_of(P, cx, a);
@@ -360,7 +378,8 @@ static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
 // (ni >= 0, gn_x = raw input of the norm) or a plain epilogue (+res, *dropout scale).
 static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale, double alg_macs) {
   P.macs[CAT_CONV_DGRAD] += alg_macs;
-  P.bwd.push_back([&P, ci, dy, out, ni, gn_x, res, scale](RunCtx& cx) -> int {
+  push_op(P.bwd, std::string(ni >= 0 ? "dgrad+gnrelu " : "dgrad ") + P.convs[ci].name + " " + shape_of(P, dy) + "->" + shape_of(P, out),
+          [&P, ci, dy, out, ni, gn_x, res, scale](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
     memset(&op, 0, sizeof(op));
@@ -390,7 +409,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
 }
 
 static void emit_gn_bwd_finalize(Plan& P, int ni) {
-  P.bwd.push_back([&P, ni](RunCtx& cx) -> int {
+  push_op(P.bwd, "gn_bwd_finalize " + P.norms[ni].name, [&P, ni](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
     LAUNCHED(cx, CAT_NORM, launch_gn_bwd_finalize(reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats),
                                         reinterpret_cast<float*>(cx.ws + n.coef), cx.params[n.pg], P.d.batch, n.C, n.Cld,
@@ -401,7 +420,7 @@ static void emit_gn_bwd_finalize(Plan& P, int ni) {
 }
 
 static void emit_gn_bwd(Plan& P, int ni, TRef dz, TRef x, TRef add1, TRef dx, bool scale) {
-  P.bwd.push_back([&P, ni, dz, x, add1, dx, scale](RunCtx& cx) -> int {
+  push_op(P.bwd, "gn_bwd " + P.norms[ni].name + " " + shape_of(P, x), [&P, ni, dz, x, add1, dx, scale](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
     Act a1;
     if (add1.valid()) a1 = act_of(P, cx, add1);
@@ -493,7 +512,7 @@ static int build(Plan& P) {
   const int Cp_in = round_up(d.n_features, 8);
   const int b_in = new_buf(P, N, Ds[0], Hs[0], Ws[0], Cp_in);
   need_stats(P, b_in);
-  P.fwd.push_back([&P, b_in](RunCtx& cx) -> int {
+  push_op(P.fwd, "pack_weights+input_pack", [&P, b_in](RunCtx& cx) -> int {
     B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.stats_off, 0, P.stats_bytes, cx.st));
     if (P.jobs_uploaded_for != cx.ws) {     // (re)upload the constant job tables into this workspace
       std::vector<PackJob> all(P.pack_jobs);
@@ -575,7 +594,7 @@ static int build(Plan& P) {
     s.U = slice(s.cat, 0, out_w);
     {
       TRef Pin = s.P, U = s.U;
-      P.fwd.push_back([&P, Pin, U](RunCtx& cx) -> int {
+      push_op(P.fwd, "upsample2x_fwd " + shape_of(P, Pin), [&P, Pin, U](RunCtx& cx) -> int {
         LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
                                            cx.st));
         return OK;
@@ -598,7 +617,7 @@ static int build(Plan& P) {
   }
   const TRef Xfinal = X;
   P.head_param = P.find_param("final_convolution.weight");
-  P.fwd.push_back([&P, Xfinal](RunCtx& cx) -> int {
+  push_op(P.fwd, "head_fwd", [&P, Xfinal](RunCtx& cx) -> int {
     LAUNCHED(cx, CAT_HEAD, launch_head_fwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, P.d.activation, cx.logits,
                                  cx.st));
     return OK;
@@ -607,7 +626,7 @@ static int build(Plan& P) {
   // ---------------- backward
   B200_REQUIRE(d.activation == 0, E_UNSUPPORTED,
                "plan: activation inside the model (sigmoid/softmax) is inference-only; train on logits");
-  P.bwd.push_back([&P](RunCtx& cx) -> int {
+  push_op(P.bwd, "memset", [&P](RunCtx& cx) -> int {
     B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.bz_off, 0, P.bz_bytes, cx.st));
     return OK;
   });
@@ -616,7 +635,7 @@ static int build(Plan& P) {
     const Buf xb = P.bufs[Xfinal.buf];
     g = full(P, new_buf(P, N, xb.D, xb.H, xb.W, Xfinal.c));
     TRef gg = g;
-    P.bwd.push_back([&P, Xfinal, gg](RunCtx& cx) -> int {
+    push_op(P.bwd, "head_bwd", [&P, Xfinal, gg](RunCtx& cx) -> int {
       LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits,
                                    act_of(P, cx, gg), cx.grads[P.head_param], cx.st));
       return OK;
@@ -632,7 +651,7 @@ static int build(Plan& P) {
     TRef dU = slice(g, 0, out_w);
     const Buf pb = P.bufs[s.P.buf];
     TRef dP = full(P, new_buf(P, N, pb.D, pb.H, pb.W, out_w));
-    P.bwd.push_back([&P, dU, dP](RunCtx& cx) -> int {
+    push_op(P.bwd, "upsample2x_bwd " + shape_of(P, dP), [&P, dU, dP](RunCtx& cx) -> int {
       LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
       return OK;
     });
@@ -650,7 +669,7 @@ static int build(Plan& P) {
       emit_wgrad(P, down[lj], skip[lj], g);
       TRef Z = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
       TRef gin = g;
-      P.bwd.push_back([&P, gin, Z](RunCtx& cx) -> int {
+      push_op(P.bwd, "zero_insert " + shape_of(P, Z), [&P, gin, Z](RunCtx& cx) -> int {
         LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
         return OK;
       });
@@ -662,7 +681,7 @@ static int build(Plan& P) {
     }
   }
   // weight gradients: accumulator -> torch layout (one batched launch)
-  P.bwd.push_back([&P](RunCtx& cx) -> int {
+  push_op(P.bwd, "unpack_wgrads", [&P](RunCtx& cx) -> int {
     PtrTable tbl;
     memset(&tbl, 0, sizeof(tbl));
     for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.grads[i];
@@ -773,9 +792,26 @@ int b200unet_plan_profile_begin(b200unet_plan* plan, int max_launches) {
   Prof* p = new Prof();
   p->ev.resize((size_t)max_launches * 2);
   p->cat.resize(max_launches);
+  p->label.resize(max_launches);
   for (auto& e : p->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { set_error("profile_begin: cudaEventCreate failed"); delete p; return E_CUDA; }
   plan->prof = p;
+  return OK;
+}
+
+int b200unet_plan_profile_dump(b200unet_plan* plan, const char* path) {
+  if (!plan || !plan->prof || !path) { set_error("profile_dump: not profiling"); return E_INVALID; }
+  Prof* p = plan->prof;
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error("profile_dump: cannot open %s", path); return E_INVALID; }
+  fprintf(f, "idx,category,ms,label\n");
+  for (size_t i = 0; i < p->used; ++i) {
+    if (cudaEventSynchronize(p->ev[i * 2 + 1]) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p->ev[i * 2], p->ev[i * 2 + 1]);
+    fprintf(f, "%zu,%d,%.6f,%s\n", i, p->cat[i], ms, p->label[i].c_str());
+  }
+  fclose(f);
   return OK;
 }
 

@@ -30,12 +30,13 @@ static CUtensorMapSwizzle to_cu(Swz s) {
 }
 
 int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int boxC, int boxW,
-                 int boxH, int boxD, int estride, Swz swz) {
+                 int boxH, int boxD, int estride, Swz swz, int vD, int vH, int vW) {
   EncodeTiledFn enc = get_encode();
   B200_REQUIRE(enc != nullptr, E_DRIVER, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, E_INVALID, "activation pointer not 16B aligned");
   B200_REQUIRE((ld * 2) % 16 == 0, E_INVALID, "channel pitch %d not a multiple of 8 elements", ld);
-  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(vW > 0 ? vW : W), (cuuint64_t)(vH > 0 ? vH : H),
+                        (cuuint64_t)(vD > 0 ? vD : D), (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2,
                            (cuuint64_t)D * H * W * ld * 2};
   cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)(boxW * estride), (cuuint32_t)(boxH * estride),

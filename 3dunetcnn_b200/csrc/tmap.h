@@ -9,8 +9,10 @@ enum Swz { SWZ_NONE = 0, SWZ_32 = 1, SWZ_64 = 2, SWZ_128 = 3 };
 
 // 5-D map over an NDHWC bf16 view: dims (C, W, H, D, N).  box = (boxC, boxW, boxH, boxD, 1) elements *loaded*;
 // estride = traversal stride on the three spatial dims (1, or 2 for the stride-2 convolutions).
+// vD/vH/vW (optional): "visible" spatial extents <= D/H/W.  Strides still come from D/H/W, but coordinates at or beyond
+// the visible extent read as zero (TMA out-of-bounds fill) - used to mask the padded boundary of a transposed convolution.
 int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int boxC, int boxW,
-                 int boxH, int boxD, int estride, Swz swz);
+                 int boxH, int boxD, int estride, Swz swz, int vD = 0, int vH = 0, int vW = 0);
 
 // 3-D map over packed weights [T][R][K] bf16 (K contiguous): dims (K, R, T); box (boxK, boxR, 1).
 int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz);

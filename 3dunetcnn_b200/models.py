@@ -78,6 +78,9 @@ class _Plan:
     def profile_begin(self, max_launches: int) -> None:
         _lib.check(self.lib.b200unet_plan_profile_begin(self.handle, int(max_launches)), "profile_begin")
 
+    def profile_dump(self, path: str) -> None:
+        _lib.check(self.lib.b200unet_plan_profile_dump(self.handle, path.encode()), "profile_dump")
+
     def profile_end(self):
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()

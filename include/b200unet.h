@@ -161,6 +161,8 @@ int b200unet_plan_last_launches(const b200unet_plan* plan);
 int b200unet_plan_algorithmic_macs(const b200unet_plan* plan, double* macs, int ncat);
 int b200unet_plan_profile_begin(b200unet_plan* plan, int max_launches);
 int b200unet_plan_profile_end(b200unet_plan* plan, double* ms_by_cat, int64_t* launches_by_cat, int ncat);
+/* while profiling: write one CSV row per recorded launch (index, category, milliseconds, op label) */
+int b200unet_plan_profile_dump(b200unet_plan* plan, const char* path);
 
 /* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
 int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
