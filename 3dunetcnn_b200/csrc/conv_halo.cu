@@ -27,17 +27,20 @@ struct HaloCfg {
   static constexpr int NHALO = 2;
   static constexpr int B_TX = BN * KC * 2;
   static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
-  static constexpr int NB = 8;
+  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;
+  static constexpr int NB_FIT = (232448 - 1024 - AUX_BYTES - NHALO * HALO_BYTES) / B_BYTES;
+  static constexpr int NB = NB_FIT > 24 ? 24 : NB_FIT;      // weight tiles in flight: latency / (MMA time per tap)
   static constexpr int NACC = (2 * TD * BN <= 512) ? 2 : 1;
   static constexpr int ACC_COLS = NACC * TD * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;
   static constexpr int SMEM_BYTES = NHALO * HALO_BYTES + NB * B_BYTES + AUX_BYTES + 1024;
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
   static constexpr uint32_t SBO_B = 8 * RB;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
+  static_assert(NB >= 4, "weight ring too shallow");
+  static_assert((2 * NHALO + 2 * NB + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
 };
 
 struct HaloArgs {

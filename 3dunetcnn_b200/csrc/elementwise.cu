@@ -189,24 +189,46 @@ int launch_gn_finalize(const double* stats, const float* gamma, const float* bet
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm apply (+ReLU / LeakyReLU)
-__global__ void k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope) {
+// grid (blocks, N); a thread keeps the same 8-channel chunk for its whole grid-stride loop (blockDim.x % c8n == 0),
+// so the affine coefficients live in registers and the loop body is load -> 8 FMA/max -> store, two voxels in flight.
+__global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope) {
   const int c8n = x.C / 8;
+  const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
-  const long long total = (long long)x.N * S * c8n;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(t % c8n);
-    const long long vox = t / c8n;
-    const int n = (int)(vox / S);
-    float v[8];
-    load8(x.hi, x.lo, vox * x.ld + c8 * 8, v);
-    const float4* cf = coef + (long long)n * x.C + c8 * 8;
+  const int c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n;
+  const int vper = blockDim.x / c8n;
+  float ka[8], kb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
+    ka[j] = k.x; kb[j] = k.y;
+  }
+  const long long base = (long long)n * S;
+  const long long stride = (long long)gridDim.x * vper;
+  long long s = (long long)blockIdx.x * vper + vslot;
+  for (; s + stride < S; s += 2 * stride) {
+    float v0[8], v1[8];
+    load8(x.hi, x.lo, (base + s) * x.ld + c8 * 8, v0);
+    load8(x.hi, x.lo, (base + s + stride) * x.ld + c8 * 8, v1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 k = __ldg(cf + j);
-      float z = fmaf(k.x, v[j], k.y);
-      v[j] = z > 0.f ? z : z * slope;
+      const float z0 = fmaf(ka[j], v0[j], kb[j]), z1 = fmaf(ka[j], v1[j], kb[j]);
+      v0[j] = z0 > 0.f ? z0 : z0 * slope;
+      v1[j] = z1 > 0.f ? z1 : z1 * slope;
     }
-    store8(y.hi, y.lo, vox * y.ld + c8 * 8, v);
+    store8(y.hi, y.lo, (base + s) * y.ld + c8 * 8, v0);
+    store8(y.hi, y.lo, (base + s + stride) * y.ld + c8 * 8, v1);
+  }
+  if (s < S) {
+    float v0[8];
+    load8(x.hi, x.lo, (base + s) * x.ld + c8 * 8, v0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z0 = fmaf(ka[j], v0[j], kb[j]);
+      v0[j] = z0 > 0.f ? z0 : z0 * slope;
+    }
+    store8(y.hi, y.lo, (base + s) * y.ld + c8 * 8, v0);
   }
 }
 
@@ -216,10 +238,24 @@ static int ew_blocks(long long total, int threads) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// threads per block: multiple of c8n (and of 32), close to 256
+static int ew_threads_for(int c8n) {
+  int t = 256;
+  while (t % c8n) t += 32;
+  return t;
+}
+
 int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st) {
   B200_REQUIRE(x.C % 8 == 0 && y.C == x.C, E_INVALID, "gn_apply: C=%d/%d", x.C, y.C);
-  long long total = x.voxels() * (x.C / 8);
-  k_gn_apply<<<ew_blocks(total, 256), 256, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope);
+  const int c8n = x.C / 8;
+  const int threads = ew_threads_for(c8n);
+  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "gn_apply: C=%d unsupported", x.C);
+  const long long S = (long long)x.D * x.H * x.W;
+  const int vper = threads / c8n;
+  long long want = (S + 2LL * vper - 1) / (2LL * vper);
+  const long long cap = (148LL * 8 + x.N - 1) / x.N;
+  int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  k_gn_apply<<<dim3(blocks, x.N), threads, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -270,27 +306,33 @@ int launch_gn_bwd_finalize(const double* bstats, const float* coef, const float*
   return OK;
 }
 
-// dx = A*dz + E*x + F (+ add1) (+ add2)
-__global__ void k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef, const float2* __restrict__ coef2, Act add1,
-                         Act add2, Act dx, const float* __restrict__ scale) {
+// dx = (A*dz + E*x + F (+ add1) (+ add2)) [* scale]     grid (blocks, N), per-thread constant channel chunk
+__global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef,
+                                                const float2* __restrict__ coef2, Act add1, Act add2, Act dx,
+                                                const float* __restrict__ scale) {
   const int c8n = x.C / 8;
+  const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
-  const long long total = (long long)x.N * S * c8n;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(t % c8n);
-    const long long vox = t / c8n;
-    const int n = (int)(vox / S);
+  const int c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n;
+  const int vper = blockDim.x / c8n;
+  float ka[8], ke[8], kf[8], ks[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
+    const float2 e = __ldg(coef2 + (long long)n * x.C + c8 * 8 + j);
+    ka[j] = k.x; ke[j] = e.x; kf[j] = e.y;
+    ks[j] = scale ? __ldg(scale + (long long)n * x.C + c8 * 8 + j) : 1.f;
+  }
+  const long long base = (long long)n * S;
+  const long long stride = (long long)gridDim.x * vper;
+  for (long long s = (long long)blockIdx.x * vper + vslot; s < S; s += stride) {
+    const long long vox = base + s;
     float g[8], v[8], o[8];
     load8(dz.hi, dz.lo, vox * dz.ld + c8 * 8, g);
     load8(x.hi, x.lo, vox * x.ld + c8 * 8, v);
-    const float4* cf = coef + (long long)n * x.C + c8 * 8;
-    const float2* cf2 = coef2 + (long long)n * x.C + c8 * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 k = __ldg(cf + j);
-      float2 e = __ldg(cf2 + j);
-      o[j] = fmaf(k.x, g[j], fmaf(e.x, v[j], e.y));
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(ka[j], g[j], fmaf(ke[j], v[j], kf[j]));
     if (add1.hi) {
       float a[8];
       load8(add1.hi, add1.lo, vox * add1.ld + c8 * 8, a);
@@ -303,10 +345,8 @@ __global__ void k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef, const f
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += a[j];
     }
-    if (scale) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] *= __ldg(scale + (long long)n * x.C + c8 * 8 + j);
-    }
+    for (int j = 0; j < 8; ++j) o[j] *= ks[j];
     store8(dx.hi, dx.lo, vox * dx.ld + c8 * 8, o);
   }
 }
@@ -315,8 +355,15 @@ int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* c
                   const Act& dx, const float* scale, cudaStream_t st) {
   B200_REQUIRE(x.C % 8 == 0 && dz.C == x.C && dx.C == x.C, E_INVALID, "gn_bwd: channel mismatch");
   Act none = make_act(nullptr, nullptr, 0, 0, 0, 0, 0, 0);
-  long long total = x.voxels() * (x.C / 8);
-  k_gn_bwd<<<ew_blocks(total, 256), 256, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
+  const int c8n = x.C / 8;
+  const int threads = ew_threads_for(c8n);
+  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "gn_bwd: C=%d unsupported", x.C);
+  const long long S = (long long)x.D * x.H * x.W;
+  const int vper = threads / c8n;
+  long long want = (S + vper - 1) / vper;
+  const long long cap = (148LL * 8 + x.N - 1) / x.N;
+  int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  k_gn_bwd<<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
                                                   reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none,
                                                   add2 ? *add2 : none, dx, scale);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -356,8 +403,10 @@ __device__ __forceinline__ void up_taps(int o, int n, int& i0, int& i1, float& w
   else       { i0 = k - 1 >= 0 ? k - 1 : 0; i1 = k; w0 = 0.25f; w1 = 0.75f; }
 }
 
-__global__ void k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int stats_ld) {
-  // y dims = 2 * x dims.  thread -> (output voxel, c8)
+// Each thread produces a 2x2x2 block of outputs (o = 2k+1, 2k+2 per axis, k in [-1, n-1]) from the 2x2x2 block of
+// inputs (clamp(k), clamp(k+1)): 8 loads for 8 outputs instead of 8 loads per output.  grid (blocks, N); the 8-channel
+// chunk is constant per thread, so the per-channel statistics accumulate in registers.
+__global__ void __launch_bounds__(256) k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int stats_ld) {
   const int c8n = x.C / 8;
   extern __shared__ float sm[];  // [C][2]
   if (stats) {
@@ -365,43 +414,47 @@ __global__ void k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int s
     __syncthreads();
   }
   const int n = blockIdx.y;
-  const long long So = (long long)y.D * y.H * y.W;
-  const long long total = So * c8n;
+  const int c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n;
+  const int vper = blockDim.x / c8n;
+  const int bw = x.W + 1, bh = x.H + 1, bd = x.D + 1;
+  const int nblk = bw * bh * bd;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
-  int my_c8 = -1;
-  // blockDim.x is a multiple of c8n so that a thread keeps the same c8 across iterations
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(t % c8n);
-    my_c8 = c8;
-    long long vo = t / c8n;
-    const int ow = (int)(vo % y.W); vo /= y.W;
-    const int oh = (int)(vo % y.H);
-    const int od = (int)(vo / y.H);
-    int d0, d1, h0, h1, w0, w1; float wd0, wd1, wh0, wh1, ww0, ww1;
-    up_taps(od, x.D, d0, d1, wd0, wd1);
-    up_taps(oh, x.H, h0, h1, wh0, wh1);
-    up_taps(ow, x.W, w0, w1, ww0, ww1);
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  for (int t = blockIdx.x * vper + vslot; t < nblk; t += gridDim.x * vper) {
+    const int kw = t % bw - 1, kh = (t / bw) % bh - 1, kd = t / (bw * bh) - 1;
+    const int w0 = kw < 0 ? 0 : kw, w1 = kw + 1 < x.W ? kw + 1 : x.W - 1;
+    const int h0 = kh < 0 ? 0 : kh, h1 = kh + 1 < x.H ? kh + 1 : x.H - 1;
+    const int d0 = kd < 0 ? 0 : kd, d1 = kd + 1 < x.D ? kd + 1 : x.D - 1;
+    float v[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int d = (i & 4) ? d1 : d0, h = (i & 2) ? h1 : h0, w = (i & 1) ? w1 : w0;
-      const float wt = ((i & 4) ? wd1 : wd0) * ((i & 2) ? wh1 : wh0) * ((i & 1) ? ww1 : ww0);
-      float v[8];
-      load8(x.hi, x.lo, ((((long long)n * x.D + d) * x.H + h) * x.W + w) * x.ld + c8 * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(wt, v[j], o[j]);
+      load8(x.hi, x.lo, ((((long long)n * x.D + d) * x.H + h) * x.W + w) * x.ld + c8 * 8, v[i]);
     }
-    store8(y.hi, y.lo, ((((long long)n * y.D + od) * y.H + oh) * y.W + ow) * y.ld + c8 * 8, o);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] += o[j]; b[j] += o[j] * o[j]; }
+    for (int o = 0; o < 8; ++o) {
+      const int od = 2 * kd + 1 + ((o >> 2) & 1), oh = 2 * kh + 1 + ((o >> 1) & 1), ow = 2 * kw + 1 + (o & 1);
+      if (od < 0 || oh < 0 || ow < 0 || od >= y.D || oh >= y.H || ow >= y.W) continue;
+      // output 2k+1 = .75 x[k] + .25 x[k+1] ; output 2k+2 = .25 x[k] + .75 x[k+1]
+      const float wd1 = (o & 4) ? 0.75f : 0.25f, wh1 = (o & 2) ? 0.75f : 0.25f, ww1 = (o & 1) ? 0.75f : 0.25f;
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float wt = ((i & 4) ? wd1 : 1.f - wd1) * ((i & 2) ? wh1 : 1.f - wh1) * ((i & 1) ? ww1 : 1.f - ww1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(wt, v[i][j], r[j]);
+      }
+      store8(y.hi, y.lo, ((((long long)n * y.D + od) * y.H + oh) * y.W + ow) * y.ld + c8 * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += r[j]; b[j] = fmaf(r[j], r[j], b[j]); }
+    }
   }
   if (stats) {
     const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;   // then lanes l, l' share the chunk iff l % c8n == l' % c8n
-    const int lane_c8 = threadIdx.x % c8n;                    // == my_c8 for every thread that did work
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float pa = a[j], pb = b[j];
@@ -411,12 +464,12 @@ __global__ void k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int s
           pb += __shfl_xor_sync(0xffffffffu, pb, off);
         }
         if ((threadIdx.x & 31) < c8n) {
-          atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 0], pa);
-          atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 1], pb);
+          atomicAdd(&sm[(c8 * 8 + j) * 2 + 0], pa);
+          atomicAdd(&sm[(c8 * 8 + j) * 2 + 1], pb);
         }
-      } else if (my_c8 >= 0) {
-        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 0], pa);
-        atomicAdd(&sm[(my_c8 * 8 + j) * 2 + 1], pb);
+      } else {
+        atomicAdd(&sm[(c8 * 8 + j) * 2 + 0], pa);
+        atomicAdd(&sm[(c8 * 8 + j) * 2 + 1], pb);
       }
     }
     __syncthreads();
@@ -429,12 +482,14 @@ int launch_upsample2x_fwd(const Act& x, const Act& y, double* stats, int stats_l
   B200_REQUIRE(y.D == 2 * x.D && y.H == 2 * x.H && y.W == 2 * x.W, E_UNSUPPORTED,
                "upsample: output must be exactly 2x (got %dx%dx%d -> %dx%dx%d)", x.D, x.H, x.W, y.D, y.H, y.W);
   const int c8n = x.C / 8;
-  int threads = 256;
-  while (threads % c8n) threads += 32;
+  const int threads = ew_threads_for(c8n);
   B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "upsample: C=%d unsupported", x.C);
-  long long total = (long long)y.D * y.H * y.W * c8n;
-  int blocks = ew_blocks(total, threads);
-  // grid-stride must preserve c8 per thread: gridDim.x*blockDim.x % c8n == 0 holds since blockDim % c8n == 0
+  const int vper = threads / c8n;
+  const long long nblk = (long long)(x.D + 1) * (x.H + 1) * (x.W + 1);
+  B200_REQUIRE(nblk < (1LL << 31), E_UNSUPPORTED, "upsample: volume too large");
+  long long want = (nblk + vper - 1) / vper;
+  const long long cap = (148LL * 8 + x.N - 1) / x.N;
+  const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   k_upsample2x_fwd<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(float), st>>>(x, y, stats, stats_ld);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
