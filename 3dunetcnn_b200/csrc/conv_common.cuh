@@ -27,6 +27,8 @@ struct ConvArgs {
   const float4* coef; int coef_ld;
   float slope;
   double* bstats;
+  const float* bias;   // optional per-output-channel bias (ConvTranspose3d, decoder.py:101-102)
+  int zero_last;       // force the high boundary plane/row/column of the output to exactly 0 (F.pad after ConvT, unet.py:38)
 };
 
 __device__ __forceinline__ void epi_load8(const bf16* hi, const bf16* lo, long long off, float* v) {
@@ -109,7 +111,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const ConvArgs& p, int n0
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t tacc, int lane_base, int lane, int n,
                                                    int n0, long long vox, bool valid, float* s_stats,
-                                                   const float4* s_coef, bool want_stats) {
+                                                   const float4* s_coef, bool want_stats, bool edge = false) {
   constexpr int G = BN < 64 ? BN : 64;
   const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
   const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
@@ -164,6 +166,14 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t t
               if (p.scale) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
+              }
+              if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += __ldg(p.bias + cc + i);
+              }
+              if (edge) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = 0.f;
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) qq[i] = vv[i] * vv[i];

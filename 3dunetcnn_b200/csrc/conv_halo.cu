@@ -323,6 +323,14 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
 #pragma unroll
                     for (int i = 0; i < 8; ++i) vv[i] *= __ldg(p.scale + (long long)n * p.Cout + cc + i);
                   }
+                  if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vv[i] += __ldg(p.bias + cc + i);
+                  }
+                  if (p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d0 + dpl == p.Do - 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vv[i] = 0.f;
+                  }
 #pragma unroll
                   for (int i = 0; i < 8; ++i) { as_[hf * 8 + i] += vv[i]; aq_[hf * 8 + i] = fmaf(vv[i], vv[i], aq_[hf * 8 + i]); }
                 } else {
@@ -458,10 +466,10 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     const ConvSrc& c = op.src[s];
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = 1;
     a.kchunks[s] = ceil_div(c.x.C, KC);
-    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz));
+    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz, c.x.vD, c.x.vH, c.x.vW));
     B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     if (split) {
-      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz));
+      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz, c.x.vD, c.x.vH, c.x.vW));
       B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     }
   }
@@ -473,6 +481,7 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     a.res_hi = op.res->hi; a.res_lo = op.res->lo; a.ldr = op.res->ld;
   }
   a.scale = op.scale;
+  a.bias = op.bias; a.zero_last = op.zero_last;
   a.stats = op.stats; a.stats_ld = op.stats_ld;
   if (op.mode == 1) {
     B200_REQUIRE(op.gn_x && op.coef, E_INVALID, "conv_halo: mode 1 needs gn_x and coef");

@@ -745,12 +745,14 @@ __global__ void k_pack_all(PtrTable params, const PackJob* __restrict__ jobs, ui
   const long long total = (long long)j.T * j.Cop * j.Cip;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (j.mode == 0) {
+    if (j.mode == 0 || j.mode == 2) {
       const int ci = (int)(i % j.Cip); const int co = (int)((i / j.Cip) % j.Cop); const int t = (int)(i / ((long long)j.Cip * j.Cop));
-      if (ci < j.Ci && co < j.Co) v = w[((long long)co * j.Ci + ci) * j.T + t];
+      if (ci < j.Ci && co < j.Co)
+        v = j.mode == 0 ? w[((long long)co * j.Ci + ci) * j.T + t] : w[((long long)ci * j.Co + co) * j.T + (j.T - 1 - t)];
     } else {
       const int co = (int)(i % j.Cop); const int ci = (int)((i / j.Cop) % j.Cip); const int t = (int)(i / ((long long)j.Cip * j.Cop));
-      if (ci < j.Ci && co < j.Co) v = w[((long long)co * j.Ci + ci) * j.T + (j.T - 1 - t)];
+      if (ci < j.Ci && co < j.Co)
+        v = j.mode == 1 ? w[((long long)co * j.Ci + ci) * j.T + (j.T - 1 - t)] : w[((long long)ci * j.Co + co) * j.T + t];
     }
     bf16 h = __float2bfloat16_rn(v);
     hi[i] = h;
@@ -771,14 +773,60 @@ __global__ void k_unpack_all(PtrTable grads, const PackJob* __restrict__ jobs, c
   const float* __restrict__ g = reinterpret_cast<const float*>(ws + j.off_hi);   // fp32 accumulator [T][Cip][Cop]
   const long long total = (long long)j.T * j.Co * j.Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % j.T); const int ci = (int)((i / j.T) % j.Ci); const int co = (int)(i / ((long long)j.T * j.Ci));
-    out[i] = g[((long long)t * j.Cip + ci) * j.Cop + co];
+    if (j.mode == 0) {
+      const int t = (int)(i % j.T); const int ci = (int)((i / j.T) % j.Ci); const int co = (int)(i / ((long long)j.T * j.Ci));
+      out[i] = g[((long long)t * j.Cip + ci) * j.Cop + co];
+    } else {   // ConvTranspose3d gradient layout [Ci][Co][T], taps flipped back
+      const int t = (int)(i % j.T); const int co = (int)((i / j.T) % j.Co); const int ci = (int)(i / ((long long)j.T * j.Co));
+      out[i] = g[((long long)(j.T - 1 - t) * j.Cip + ci) * j.Cop + co];
+    }
   }
 }
 
 int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st) {
   if (njobs == 0) return OK;
   k_unpack_all<<<dim3(48, njobs), 256, 0, st>>>(grads, jobs_dev, ws);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------ bias gradient
+// dbias[c] = sum over the visible voxels (d < vD, h < vH, w < vW) of dy[v][c]   (ConvTranspose3d bias; the padded
+// boundary of its output is a constant and carries no gradient)
+__global__ void k_bias_grad(Act dy, float* __restrict__ dbias) {
+  const int c8n = dy.C / 8;
+  const int c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n, vper = blockDim.x / c8n;
+  const int vD = dy.vD > 0 ? dy.vD : dy.D, vH = dy.vH > 0 ? dy.vH : dy.H, vW = dy.vW > 0 ? dy.vW : dy.W;
+  const long long total = dy.voxels();
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (long long v = (long long)blockIdx.x * vper + vslot; v < total; v += (long long)gridDim.x * vper) {
+    const int w = (int)(v % dy.W), h = (int)((v / dy.W) % dy.H), d = (int)((v / ((long long)dy.W * dy.H)) % dy.D);
+    if (w >= vW || h >= vH || d >= vD) continue;
+    float g[8];
+    load8(dy.hi, dy.lo, v * dy.ld + c8 * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += g[j];
+  }
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < dy.C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&sm[c8 * 8 + j], a[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < dy.C; i += blockDim.x) atomicAdd(&dbias[i], sm[i]);
+}
+
+int launch_bias_grad(const Act& dy, float* dbias, cudaStream_t st) {
+  B200_REQUIRE(dy.C % 8 == 0, E_INVALID, "bias_grad: C=%d", dy.C);
+  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * dy.C, st));
+  const int threads = ew_threads_for(dy.C / 8);
+  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "bias_grad: C=%d unsupported", dy.C);
+  long long want = (dy.voxels() + threads / (dy.C / 8) - 1) / (threads / (dy.C / 8));
+  int blocks = (int)(want < 592 ? (want > 0 ? want : 1) : 592);
+  k_bias_grad<<<blocks, threads, dy.C * sizeof(float), st>>>(dy, dbias);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
-    conv_epilogue_tile<BN>(p, tmem_base, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats);
+    const bool edge = p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d == p.Do - 1);
+    conv_epilogue_tile<BN>(p, tmem_base, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge);
     tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (want_stats) {
@@ -256,11 +257,11 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = c.stride;
     a.kchunks[s] = ceil_div(c.x.C, KC);
     B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
-                          c.stride, swz));
+                          c.stride, swz, c.x.vD, c.x.vH, c.x.vW));
     B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     if (split) {
       B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
-                            c.stride, swz));
+                            c.stride, swz, c.x.vD, c.x.vH, c.x.vW));
       B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     }
   }
@@ -272,6 +273,7 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     a.res_hi = op.res->hi; a.res_lo = op.res->lo; a.ldr = op.res->ld;
   }
   a.scale = op.scale;
+  a.bias = op.bias; a.zero_last = op.zero_last;
   a.stats = op.stats; a.stats_ld = op.stats_ld;
   if (op.mode == 1) {
     B200_REQUIRE(op.gn_x && op.coef, E_INVALID, "igemm_conv: mode 1 needs gn_x and coef");

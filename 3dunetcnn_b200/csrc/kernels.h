@@ -29,11 +29,14 @@ struct PtrTable { const void* p[256]; };
 struct PackJob {
   int pidx;                 // index into the parameter / gradient pointer table
   int Co, Ci, Cop, Cip, T;
-  int mode;                 // 0 forward [T][Cop][Cip], 1 data-gradient [T][Cip][Cop] flipped
+  int mode;                 // 0 forward [T][Cop][Cip], 1 data-gradient [T][Cip][Cop] flipped; ConvTranspose3d weight
+                            // [Ci][Co][T]: 2 forward [T][Cop][Cip] flipped, 3 data-gradient [T][Cip][Cop] unflipped;
+                            // unpack: 0 -> [Co][Ci][T], 2 -> [Ci][Co][T] flipped
   long long off_hi, off_lo; // workspace byte offsets (unpack: off_hi = fp32 accumulator)
 };
 int launch_pack_all(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st);
 int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st);
+int launch_bias_grad(const Act& dy, float* dbias, cudaStream_t st);   // dbias[c] = sum over the VISIBLE voxels of dy
 int launch_zero_insert(const Act& x, const Act& z, int od, int oh, int ow, cudaStream_t st);
 int launch_ncdhw_to_act(const float* x, int C, const Act& out, cudaStream_t st);
 int launch_act_to_ncdhw(const Act& in, int C, float* y, cudaStream_t st);
@@ -73,6 +76,8 @@ struct ConvOp {
   int coef_ld;
   float slope;         // mode 1: negative slope of the activation (0 = ReLU)
   double* bstats;      // mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat)
+  const float* bias;   // mode 0: optional per-channel bias
+  int zero_last;       // mode 0: output voxels on the high boundary of each axis are forced to 0
 };
 
 int launch_igemm_conv(const ConvOp& op, cudaStream_t st);   // dispatcher: halo-resident kernel when eligible

@@ -33,9 +33,10 @@ struct Buf {
 struct TRef {
   int buf;
   int c0, c;
+  int vis_m1;   // 1: the last plane/row/column is masked (reads as zero through TMA): dU of a padded ConvTranspose3d
   bool valid() const { return buf >= 0; }
 };
-static const TRef kNone = {-1, 0, 0};
+static const TRef kNone = {-1, 0, 0, 0};
 
 struct RunCtx {
   uint8_t* ws;
@@ -68,6 +69,8 @@ struct ConvLayer {
   size_t wd_hi, wd_lo;     // packed data-grad weights [T][Cip][Cop]
   size_t dw;               // fp32 accumulator         [T][Cip][Cop]
   bool need_dgrad;
+  bool transposed;         // nn.ConvTranspose3d weight [Ci][Co][T] (+ bias parameter pb)
+  int pb;
   std::string name;        // state-dict key (profiling labels)
 };
 
@@ -93,6 +96,8 @@ struct StageRec {  // decoder up-sampling stage
   TRef U;          // up-sampled slice of the concat buffer
   TRef cat;        // full concat view
   int cpre;
+  TRef Z;          // transposed-convolution decoder: zero-inserted input (full resolution)
+  int cup;         // transposed-convolution layer (-1 in trilinear mode)
 };
 
 typedef std::function<int(RunCtx&)> OpFn;
@@ -230,14 +235,17 @@ static int new_buf(Plan& P, int N, int D, int H, int W, int C) {
   return (int)P.bufs.size() - 1;
 }
 
-static TRef full(const Plan& P, int buf) { TRef t = {buf, 0, P.bufs[buf].C}; return t; }
-static TRef slice(TRef t, int c0, int c) { TRef r = {t.buf, t.c0 + c0, c}; return r; }
+static TRef full(const Plan& P, int buf) { TRef t = {buf, 0, P.bufs[buf].C, 0}; return t; }
+static TRef slice(TRef t, int c0, int c) { TRef r = {t.buf, t.c0 + c0, c, t.vis_m1}; return r; }
+static TRef masked(TRef t) { TRef r = t; r.vis_m1 = 1; return r; }
 
 static Act act_of(const Plan& P, const RunCtx& cx, TRef t) {
   const Buf& b = P.bufs[t.buf];
   bf16* hi = reinterpret_cast<bf16*>(cx.ws + b.off_hi) + t.c0;
   bf16* lo = P.split ? reinterpret_cast<bf16*>(cx.ws + b.off_lo) + t.c0 : nullptr;
-  return make_act(hi, lo, b.N, b.D, b.H, b.W, t.c, b.C);
+  Act a = make_act(hi, lo, b.N, b.D, b.H, b.W, t.c, b.C);
+  if (t.vis_m1) { a.vD = b.D - 1; a.vH = b.H - 1; a.vW = b.W - 1; }
+  return a;
 }
 
 static void need_stats(Plan& P, int buf) {
@@ -258,6 +266,8 @@ static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, in
   c.Co = Co; c.Ci = Ci; c.Cop = round_up(Co, 8); c.Cip = round_up(Ci, 8);
   c.ksz = ksz; c.stride = stride; c.T = ksz * ksz * ksz;
   c.need_dgrad = need_dgrad;
+  c.transposed = false;
+  c.pb = -1;
   size_t n = (size_t)c.T * c.Cop * c.Cip;
   c.wf_hi = P.alloc(n * 2);
   c.wf_lo = P.split ? P.alloc(n * 2) : 0;
@@ -324,7 +334,7 @@ static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
 static double conv_macs(const Plan& P, int ci, TRef out_like) {
   const ConvLayer& c = P.convs[ci];
   const Buf& b = P.bufs[out_like.buf];
-  return (double)b.N * b.D * b.H * b.W * c.Co * c.Ci * c.T;
+  return (double)b.N * b.D * b.H * b.W * c.Co * c.Ci * c.T / (c.transposed ? 8.0 : 1.0);
 }
 
 static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, TRef out, bool stats, bool scale) {
@@ -354,6 +364,7 @@ static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, T
     if (res.valid()) { r = act_of(P, cx, res); op.res = &r; }
     if (scale && cx.drop) op.scale = cx.drop;
     if (stats) { op.stats = stats_ptr(P, cx, out); op.stats_ld = P.bufs[out.buf].C; }
+    if (c.transposed) { op.bias = cx.params[c.pb]; op.zero_last = 1; }
     LAUNCHED(cx, CAT_CONV_FWD, launch_igemm_conv(op, cx.st));
     return OK;
   });
@@ -387,7 +398,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
     op.src[0].x = act_of(P, cx, dy);
     op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wd_hi);
     op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr;
-    op.src[0].ksz = c.ksz; op.src[0].stride = 1; op.src[0].Cip = c.Cop;  // K extent of Wd = Cop
+    op.src[0].ksz = c.ksz; op.src[0].stride = c.transposed ? 2 : 1; op.src[0].Cip = c.Cop;  // K extent of Wd = Cop
     op.Cop = c.Cip;                                                       // rows of Wd = Cip
     op.out = act_of(P, cx, out);
     Act r, gx;
@@ -490,7 +501,6 @@ static int build(Plan& P) {
   const b200unet_net_desc& d = P.d;
   const int L = d.n_levels, N = d.batch;
   B200_REQUIRE(L >= 2 && L <= 8, E_UNSUPPORTED, "plan: n_levels=%d unsupported (2..8)", L);
-  B200_REQUIRE(!d.use_transposed_convolutions, E_UNSUPPORTED, "plan: use_transposed_convolutions not implemented yet");
   B200_REQUIRE(d.base_width % 8 == 0, E_UNSUPPORTED, "plan: base_width=%d must be a multiple of 8", d.base_width);
   B200_REQUIRE(d.n_features >= 1 && d.n_features <= 16, E_UNSUPPORTED, "plan: n_features=%d unsupported", d.n_features);
   B200_REQUIRE(d.n_outputs >= 1 && d.n_outputs <= 8, E_UNSUPPORTED, "plan: n_outputs=%d unsupported", d.n_outputs);
@@ -586,19 +596,35 @@ static int build(Plan& P) {
     B200_REQUIRE(out_w == widths[j], E_INVALID, "plan: decoder stage %d width mismatch", i);
     StageRec s;
     s.Xin = X;
-    s.cpre = new_conv(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", out_w, in_w, 1, 1, true);
-    emit_pack(P, s.cpre);
-    s.P = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
-    emit_conv_fwd(P, s.cpre, X, -1, kNone, kNone, s.P, false, false);
     s.cat = full(P, cat[j]);
     s.U = slice(s.cat, 0, out_w);
-    {
+    s.cpre = -1; s.cup = -1; s.P = kNone; s.Z = kNone;
+    if (!d.use_transposed_convolutions) {
+      s.cpre = new_conv(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", out_w, in_w, 1, 1, true);
+      emit_pack(P, s.cpre);
+      s.P = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
+      emit_conv_fwd(P, s.cpre, X, -1, kNone, kNone, s.P, false, false);
       TRef Pin = s.P, U = s.U;
       push_op(P.fwd, "upsample2x_fwd " + shape_of(P, Pin), [&P, Pin, U](RunCtx& cx) -> int {
         LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
                                            cx.st));
         return OK;
       });
+    } else {
+      // ConvTranspose3d(k3, s2, p1) + bias, then F.pad(+1 high side) = zero-insert + 3x3x3 conv with the flipped
+      // kernel over a 2n grid whose last plane/row/column is forced to 0 (decoder.py:101-102, unet.py:34-40)
+      const std::string key = "decoder.upsampling_blocks." + std::to_string(i);
+      s.cup = new_conv(P, key + ".weight", out_w, in_w, 3, 1, true);
+      P.convs[s.cup].transposed = true;
+      P.convs[s.cup].pb = P.find_param(key + ".bias");
+      B200_REQUIRE(P.convs[s.cup].pb >= 0, E_INVALID, "plan: internal: missing bias for %s", key.c_str());
+      s.Z = full(P, new_buf(P, N, 2 * xb.D, 2 * xb.H, 2 * xb.W, in_w));
+      TRef Xi = X, Z = s.Z;
+      push_op(P.fwd, "zero_insert " + shape_of(P, Z), [&P, Xi, Z](RunCtx& cx) -> int {
+        LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, Xi), act_of(P, cx, Z), 0, 0, 0, cx.st));
+        return OK;
+      });
+      emit_conv_fwd(P, s.cup, s.Z, -1, kNone, kNone, s.U, true, false);
     }
     stages.push_back(s);
     X = s.cat;
@@ -649,15 +675,27 @@ static int build(Plan& P) {
     const int out_w = s.U.c;
     dskip_dec[j] = slice(g, out_w, out_w);
     TRef dU = slice(g, 0, out_w);
-    const Buf pb = P.bufs[s.P.buf];
-    TRef dP = full(P, new_buf(P, N, pb.D, pb.H, pb.W, out_w));
-    push_op(P.bwd, "upsample2x_bwd " + shape_of(P, dP), [&P, dU, dP](RunCtx& cx) -> int {
-      LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
-      return OK;
-    });
-    emit_wgrad(P, s.cpre, s.Xin, dP);
-    TRef gX = full(P, new_buf(P, N, pb.D, pb.H, pb.W, s.Xin.c));
-    emit_dgrad(P, s.cpre, dP, gX, -1, kNone, kNone, false, conv_macs(P, s.cpre, dP));
+    const Buf xb = P.bufs[s.Xin.buf];
+    TRef gX = full(P, new_buf(P, N, xb.D, xb.H, xb.W, s.Xin.c));
+    if (s.cup < 0) {
+      TRef dP = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
+      push_op(P.bwd, "upsample2x_bwd " + shape_of(P, dP), [&P, dU, dP](RunCtx& cx) -> int {
+        LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_bwd(act_of(P, cx, dU), act_of(P, cx, dP), cx.st));
+        return OK;
+      });
+      emit_wgrad(P, s.cpre, s.Xin, dP);
+      emit_dgrad(P, s.cpre, dP, gX, -1, kNone, kNone, false, conv_macs(P, s.cpre, dP));
+    } else {
+      // the padded boundary of the ConvT output is a constant: mask it out of dU (visible extent 2n-1 through TMA)
+      TRef dUm = masked(dU);
+      const int cup = s.cup;
+      push_op(P.bwd, "bias_grad " + P.convs[cup].name, [&P, dUm, cup](RunCtx& cx) -> int {
+        LAUNCHED(cx, CAT_OTHER, launch_bias_grad(act_of(P, cx, dUm), cx.grads[P.convs[cup].pb], cx.st));
+        return OK;
+      });
+      emit_wgrad(P, cup, s.Z, dUm);                                   // dW[tap][ci][co] from the zero-inserted input
+      emit_dgrad(P, cup, dUm, gX, -1, kNone, kNone, false, conv_macs(P, cup, dUm));   // stride-2 conv of dU: dX[i] = sum_k dU[2i+k-1] W[ci][co][k]
+    }
     for (int b = d.decoder_blocks[i] - 1; b >= 0; --b) gX = build_block_bwd(P, dec[i][b], gX);
     g = gX;
   }
@@ -699,11 +737,14 @@ static int build(Plan& P) {
   for (const ConvLayer& c : P.convs) {
     PackJob j;
     j.pidx = c.pw; j.Co = c.Co; j.Ci = c.Ci; j.Cop = c.Cop; j.Cip = c.Cip; j.T = c.T;
-    j.mode = 0; j.off_hi = (long long)c.wf_hi; j.off_lo = (long long)c.wf_lo;
+    j.mode = c.transposed ? 2 : 0; j.off_hi = (long long)c.wf_hi; j.off_lo = (long long)c.wf_lo;
     P.pack_jobs.push_back(j);
-    if (c.need_dgrad) { j.mode = 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo; P.pack_jobs.push_back(j); }
+    if (c.need_dgrad) {
+      j.mode = c.transposed ? 3 : 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo;
+      P.pack_jobs.push_back(j);
+    }
     PackJob u = j;
-    u.mode = 0; u.off_hi = (long long)(P.bz_off + c.dw); u.off_lo = 0;
+    u.mode = c.transposed ? 2 : 0; u.off_hi = (long long)(P.bz_off + c.dw); u.off_lo = 0;
     P.unpack_jobs.push_back(u);
   }
   P.jobs_off = P.alloc(sizeof(PackJob) * (P.pack_jobs.size() + P.unpack_jobs.size()));

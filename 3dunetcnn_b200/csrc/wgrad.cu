@@ -289,14 +289,14 @@ int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st) {
   a.npass = split ? 3 : 1;
   a.dw = op.dw;
   B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, CB, a.tw, a.th, a.td, op.stride,
-                        swz_for_bytes(CB * 2)));
+                        swz_for_bytes(CB * 2), A.vD, A.vH, A.vW));
   B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, a.tw, a.th, a.td, 1,
-                        swz_for_bytes(CBN * 2)));
+                        swz_for_bytes(CBN * 2), Y.vD, Y.vH, Y.vW));
   if (split) {
     B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, CB, a.tw, a.th, a.td, op.stride,
-                          swz_for_bytes(CB * 2)));
+                          swz_for_bytes(CB * 2), A.vD, A.vH, A.vW));
     B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, a.tw, a.th, a.td, 1,
-                          swz_for_bytes(CBN * 2)));
+                          swz_for_bytes(CBN * 2), Y.vD, Y.vH, Y.vW));
   }
   dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)cotiles);
 #define B200_WG_CASE(cb, bn) \

@@ -265,11 +265,11 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
     if ((v == 1 || v == 2 || v == 3 || v == 6) && ((18 / v) * 10 * KC * 2) % 128 == 0) hsplit = v;
   }
   a.hsplit = hsplit;
-  B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2)));
-  B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2)));
+  B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2), A.vD, A.vH, A.vW));
+  B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2), Y.vD, Y.vH, Y.vW));
   if (split) {
-    B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2)));
-    B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2)));
+    B200_TRY(make_act_map(&maps.a[1], A.lo, A.N, A.D, A.H, A.W, A.C, A.ld, KC, 10, 18 / hsplit, 1, 1, swz_for_bytes(KC * 2), A.vD, A.vH, A.vW));
+    B200_TRY(make_act_map(&maps.dy[1], Y.lo, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, 8, 16, 1, 1, swz_for_bytes(CBN * 2), Y.vD, Y.vH, Y.vW));
   }
   dim3 grid((unsigned)splits, (unsigned)(a.nkc * a.gpk), (unsigned)cotiles);
 #define B200_WGH_CASE(kc, bn) \

@@ -47,7 +47,8 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
-@pytest.mark.parametrize("name", ["c1_bw8_32", "c1_bw8_64", "bw16_n2_32", "c5like_1ch_5lev_32", "bw8_nonpow2_24x32x40"])
+@pytest.mark.parametrize("name", ["c1_bw8_32", "c1_bw8_64", "bw16_n2_32", "c5like_1ch_5lev_32", "bw8_nonpow2_24x32x40",
+                                  "bw8_convT_32"])
 def test_split_precision_matches_reference_goldens(pkg, golden_dir, name):
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     model, out, loss, out_eval = _run(pkg, name, "split")
@@ -106,12 +107,6 @@ def test_oracle_parity_with_encoder_variants(pkg):
     for k, p in model.named_parameters():
         r = _rel(p.grad.cpu().numpy(), sd64[k].grad.numpy())
         assert r < 5e-2, (k, r)
-
-
-def test_transposed_convolution_decoder_is_rejected_loudly(pkg):
-    model = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8, use_transposed_convolutions=True).to(DEV)
-    with pytest.raises(RuntimeError, match="use_transposed_convolutions"):
-        model(torch.zeros(1, 4, 16, 16, 16, device=DEV))
 
 
 def test_no_input_gradient_and_shape_errors(pkg):

@@ -358,6 +358,8 @@ def group_model():
         (dict(n_features=4, n_outputs=3, base_width=16), (2, 4, 32, 32, 32), "split"),
         (dict(n_features=1, n_outputs=1, base_width=8, encoder_blocks=[1, 2, 2, 4, 4]), (1, 1, 32, 32, 32), "split"),
         (dict(n_features=4, n_outputs=3, base_width=32), (2, 4, 32, 32, 32), "bf16"),
+        (dict(n_features=4, n_outputs=3, base_width=8, use_transposed_convolutions=True), (1, 4, 32, 32, 32), "split"),
+        (dict(n_features=4, n_outputs=3, base_width=16, use_transposed_convolutions=True), (2, 4, 32, 32, 32), "bf16"),
     ]:
         def t(kw=kw, shape=shape, precision=precision):
             cfg = UNetConfig(**kw)
