@@ -158,14 +158,22 @@ def test_c2_full_size_dice_matches_oracle_on_same_logits(pkg, c2):
 
 def test_c2_full_size_samples_are_independent(pkg, c2):
     """GroupNorm and Dice are per-sample: swapping the batch order must swap the outputs (the property that makes
-    the path shard over GPUs without a forward exchange)."""
+    the path shard over GPUs without a forward exchange).  The two runs reduce the GroupNorm statistics in a
+    different order (persistent CTAs, fp32 partial sums), so in bf16 storage individual roundings flip and are
+    amplified like any other bf16 noise (~1e-2); in split precision the same comparison is tight."""
     model, x, t = c2
     model.eval()
     with torch.no_grad():
         a = model(x)
         b = model(x.flip(0).contiguous())
-    r = float((a - b.flip(0)).norm() / a.norm())
-    assert r < 3e-3       # bf16 storage: atomics-order differences in the fp64 GroupNorm sums can flip roundings
+    assert float((a - b.flip(0)).norm() / a.norm()) < 2e-2
+    model_s = pkg.UNet3D(n_features=4, n_outputs=3, base_width=32, precision="split").to(DEV)
+    model_s.load_state_dict(model.state_dict())
+    model_s.eval()
+    with torch.no_grad():
+        a = model_s(x)
+        b = model_s(x.flip(0).contiguous())
+    assert float((a - b.flip(0)).norm() / a.norm()) < 1e-4
 
 
 def test_c2_full_size_backward_is_linear_in_dlogits(pkg, c2):
