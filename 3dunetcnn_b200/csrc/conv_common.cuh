@@ -10,7 +10,18 @@ namespace b200 {
 struct ConvMaps {
   CUtensorMap a[2][2];  // [source][hi/lo]
   CUtensorMap b[2][2];
+  CUtensorMap o[2];     // output tile stores (hi/lo): the epilogue stages 128 x BN tiles in shared memory and TMA-stores them
 };
+
+// Row `r` / 16-byte chunk `c` of a [128 rows][CB channels] bf16 staging tile laid out the way a TMA store with the
+// matching 32B/64B/128B swizzle expects it (absolute-address XOR; the tile base is 1024-byte aligned).
+template <int CB>
+__device__ __forceinline__ uint32_t stage_off(int r, int c) {
+  constexpr uint32_t RBO = CB * 2;
+  constexpr uint32_t MASK = RBO >= 128 ? 7u : RBO >= 64 ? 3u : 1u;
+  const uint32_t off = r * RBO + c * 16;
+  return off ^ (((off >> 7) & MASK) << 4);
+}
 
 struct ConvArgs {
   int N, Do, Ho, Wo, Cout;
@@ -111,8 +122,14 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const ConvArgs& p, int n0
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t tacc, int lane_base, int lane, int n,
                                                    int n0, long long vox, bool valid, float* s_stats,
-                                                   const float4* s_coef, bool want_stats, bool edge = false) {
+                                                   const float4* s_coef, bool want_stats, bool edge, uint8_t* stage,
+                                                   int row, bool split) {
+  // `stage`: 1024-aligned shared staging tile [BN/CBO boxes][128 rows][CBO channels] (+ the lo tile OUT_TILE bytes
+  // later in split mode); the caller TMA-stores it after a proxy fence + barrier.
   constexpr int G = BN < 64 ? BN : 64;
+  constexpr int CBO = BN < 64 ? BN : 64;
+  constexpr int OUT_BOX = 128 * CBO * 2;
+  constexpr int OUT_TILE = 128 * BN * 2;
   const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
   const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
   const int side_ld = p.mode == 0 ? p.ldr : p.ldx;
@@ -187,10 +204,25 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t t
                 qq[i] = dz * (sv[i] - k.z) * k.w;
               }
             }
-            epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { vv[i] = 0.f; qq[i] = 0.f; }
+          }
+          {
+            uint4 o;
+            o.x = pack_bf16x2(vv[0], vv[1]); o.y = pack_bf16x2(vv[2], vv[3]);
+            o.z = pack_bf16x2(vv[4], vv[5]); o.w = pack_bf16x2(vv[6], vv[7]);
+            const int col = j * 16 + hf * 8;
+            uint8_t* dst = stage + (col / CBO) * OUT_BOX + stage_off<CBO>(row, (col % CBO) / 8);
+            *reinterpret_cast<uint4*>(dst) = o;
+            if (split) {
+              uint4 l;
+              l.x = pack_bf16x2(vv[0] - bf16_lo_to_f(o.x), vv[1] - bf16_hi_to_f(o.x));
+              l.y = pack_bf16x2(vv[2] - bf16_lo_to_f(o.y), vv[3] - bf16_hi_to_f(o.y));
+              l.z = pack_bf16x2(vv[4] - bf16_lo_to_f(o.z), vv[5] - bf16_hi_to_f(o.z));
+              l.w = pack_bf16x2(vv[6] - bf16_lo_to_f(o.w), vv[7] - bf16_hi_to_f(o.w));
+              *reinterpret_cast<uint4*>(dst + OUT_TILE) = l;
+            }
           }
         }
         if (want_stats) {

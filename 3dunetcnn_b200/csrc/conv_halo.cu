@@ -1,18 +1,22 @@
 // Halo-resident implicit-GEMM convolution (3x3x3, stride 1) for sm_100a: the successor of igemm_conv.cu's per-tap
-// streaming kernel for every layer whose output plane is at least 8 x 16.
+// streaming kernel for the operand-bandwidth-bound layers (Cin <= 64) whose output plane is at least 8 x 16.
 //
 // A CTA (persistent, one per SM) walks output tiles of 8(w) x 16(h) x TD(d) voxels.  For each K chunk of KC input
-// channels it TMA-loads ONE halo box (KC, 10, 18, TD+2) of the activation into shared memory and then serves all 27
-// taps from it: tap (kd,kh,kw) of output plane d is the UMMA A operand whose descriptor START ADDRESS is shifted by
-// ((d+kd)*18 + kh)*10 + kw rows and whose 8-row-group stride (SBO) is one halo row of 10 voxels.  The hardware
-// applies the 128B/64B/32B swizzle on absolute shared-memory address bits (verified by csrc/probe.cu on B200, see
-// profiles/probe_r01.txt), so shifted / re-strided descriptors read exactly what TMA wrote.  L2->SM traffic for the
-// activation drops from 27 reads per voxel (streaming kernel) to (TD+2)/TD * 1.41.
-// Weights stream through a small ring: one (KC x BN) tile per (chunk, tap), each reused by TD output planes, i.e.
-// TD accumulators of 128 x BN fp32 live in TMEM.  With 2 accumulator sets (when 2*TD*BN <= 512 columns) the epilogue
-// of tile i overlaps the MMAs of tile i+1; two halo buffers let the next chunk/tile load under the current MMAs.
-// The optional second source (the residual block's 1x1x1 `sample`) is one more halo box read at its centre tap.
-// Epilogue: shared with igemm_conv.cu (conv_common.cuh).
+// channels it TMA-loads ONE halo box (KC, 10, 18, TD+2) of the activation into shared memory and serves all 27 taps
+// from it: tap (kd,kh,kw) of output plane d is the UMMA A operand whose descriptor START ADDRESS is shifted by
+// ((d+kd)*18 + kh)*10 + kw rows and whose 8-row-group stride (SBO) is one halo row of 10 voxels.  The hardware applies
+// the 64B/32B swizzle on absolute shared-memory address bits (verified by csrc/probe.cu on B200, profiles/probe_r01.txt),
+// so shifted / re-strided descriptors read exactly what TMA wrote.  L2->SM activation traffic drops from 27 reads per
+// voxel (streaming kernel) to (TD+2)/TD * 1.41.
+// Weights stream through a ring in groups of TPB taps (one TMA box, one barrier round-trip per group: the per-tap
+// handshake cost ~200 cycles, measured with the HALO_STAMP timeline); each weight tile is reused by TD output planes,
+// i.e. TD accumulators of 128 x BN fp32 live in TMEM, in NACC sets so the epilogue of tile i overlaps the MMAs of
+// tile i+1; two halo buffers let the next chunk / tile load under the current MMAs.
+// Issue loops are warp-convergent with one elected lane issuing (descriptors stay in uniform registers).
+// Epilogue (4 warps): TMEM -> registers -> (+residual)(*dropout)(+bias) | GroupNorm/ReLU backward -> swizzled shared
+// staging tile -> TMA store (full-line writes; the per-thread 16-byte global stores of the first version cost ~40
+// cycles per touched line and bounded every narrow layer).  Per-channel statistics accumulate in registers across
+// planes and tiles (BN <= 64) and are reduced by a transposing warp butterfly only when the sample changes.
 #include <cstdlib>
 #include "conv_common.cuh"
 
@@ -20,34 +24,44 @@ namespace b200 {
 
 template <int KC, int BN, int TD>
 struct HaloCfg {
-  static constexpr int RB = KC * 2;                         // bytes per voxel row
+  static constexpr int RB = KC * 2;                         // bytes per voxel row of the halo
   static constexpr int HALO_ROWS = 180 * (TD + 2);          // 10 x 18 x (TD+2)
   static constexpr int HALO_TX = HALO_ROWS * RB;
   static constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;
   static constexpr int NHALO = 2;
-  static constexpr int B_TX = BN * KC * 2;
-  static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
-  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;
-  static constexpr int NB_FIT = (232448 - 1024 - AUX_BYTES - NHALO * HALO_BYTES) / B_BYTES;
-  static constexpr int NB = NB_FIT > 24 ? 24 : NB_FIT;      // weight tiles in flight: latency / (MMA time per tap)
+  static constexpr int TPB = BN <= 64 ? 3 : 1;              // taps per weight stage
+  static constexpr int B_TAP = BN * KC * 2;                 // bytes of one tap's weight tile
+  static constexpr int B_TX = TPB * B_TAP;
+  static constexpr int B_BYTES = (B_TX + 1023) / 1024 * 1024;
+  static constexpr int NB_MAX = 24;
+  static constexpr int CBO = BN < 64 ? BN : 64;             // channels per output staging box
+  static constexpr int NBO = BN / CBO;
+  static constexpr int OUT_BOX = 128 * CBO * 2;
+  static constexpr int OUT_TILE = 128 * BN * 2;             // one plane, one of {hi, lo}
   static constexpr int NACC = (2 * TD * BN <= 512) ? 2 : 1;
   static constexpr int ACC_COLS = NACC * TD * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = NHALO * HALO_BYTES + NB * B_BYTES + AUX_BYTES + 1024;
+  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;   // barriers | stats | GN coefficients
+  static constexpr int BUDGET = 232448 - 1024;                   // dynamic smem limit minus alignment slack
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
   static constexpr uint32_t SBO_B = 8 * RB;
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  static constexpr bool RUN = BN <= 64;                     // register-resident running statistics
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
-  static_assert(NB >= 4, "weight ring too shallow");
-  static_assert((2 * NHALO + 2 * NB + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
+  static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
 };
 
 struct HaloArgs {
   int tiles_total;   // N * tiles_d * tiles_h * tiles_w * ntiles
   int ntiles;        // output-channel tiles
-  int hsplit;        // the halo box is loaded as (TD+2) * hsplit TMA boxes of (KC, 10, 18/hsplit, 1): more boxes in flight
+  int hsplit;        // the halo box is loaded as (TD+2) * hsplit TMA boxes of (KC, 10, 18/hsplit, 1)
+  int nb;            // weight ring depth (stages of TPB taps)
+  int nout;          // output staging buffers (1 or 2), each OUT_TILE * (split ? 2 : 1) bytes
+  int split;
+  long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
+#define HALO_STAMP(role, slot) \
+  do { if (hp.dbg && blockIdx.x == 0 && ti < 32 && lane == 0) hp.dbg[((role) * 32 + ti) * 4 + (slot)] = clock64(); } while (0)
 
 template <int KC, int BN, int TD>
 __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
@@ -55,14 +69,16 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
   using Cfg = HaloCfg<KC, BN, TD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int out_buf_bytes = Cfg::OUT_TILE * (hp.split ? 2 : 1);
   uint8_t* smem_halo = smem;
-  uint8_t* smem_b = smem + Cfg::NHALO * Cfg::HALO_BYTES;
-  uint8_t* aux = smem_b + Cfg::NB * Cfg::B_BYTES;
+  uint8_t* smem_out = smem + Cfg::NHALO * Cfg::HALO_BYTES;
+  uint8_t* smem_b = smem_out + hp.nout * out_buf_bytes;
+  uint8_t* aux = smem_b + hp.nb * Cfg::B_BYTES;
   uint64_t* halo_full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* halo_empty = halo_full + Cfg::NHALO;
   uint64_t* b_full = halo_empty + Cfg::NHALO;
-  uint64_t* b_empty = b_full + Cfg::NB;
-  uint64_t* acc_full = b_empty + Cfg::NB;
+  uint64_t* b_empty = b_full + Cfg::NB_MAX;
+  uint64_t* acc_full = b_empty + Cfg::NB_MAX;
   uint64_t* acc_empty = acc_full + Cfg::NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::NACC);
   float* s_stats = reinterpret_cast<float*>(aux + 1024);
@@ -70,15 +86,17 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t NB = hp.nb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0][0]);
     tma_prefetch_desc(&maps.b[0][0]);
+    tma_prefetch_desc(&maps.o[0]);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
-      for (int s = 0; s < Cfg::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+      for (int s = 0; s < Cfg::NB_MAX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
       for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
       fence_barrier_init();
     }
@@ -91,80 +109,89 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // K groups of one tile: source 0 = 27 taps per chunk, source 1 (optional 1x1x1) = centre tap per chunk
+  // K groups of one tile: source 0 = 27 taps per chunk (9 stages of TPB taps when TPB = 3), source 1 (optional
+  // 1x1x1) = its centre tap per chunk
   const int groups0 = p.kchunks[0], groups1 = p.ntaps[1] ? p.kchunks[1] : 0;
+  constexpr int STAGES0 = 27 / Cfg::TPB;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
-    {
-      const uint32_t issue = elect_one() ? 1u : 0u;
-      uint32_t hi = 0, bi = 0;
-      for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % hp.ntiles; t /= hp.ntiles;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h; t /= p.tiles_h;
-        const int dt = t % p.tiles_d;
-        const int n = t / p.tiles_d;
-        const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
-        for (int g = 0; g < groups0 + groups1; ++g) {
-          const int src = g < groups0 ? 0 : 1;
-          const int kc = src == 0 ? g : g - groups0;
-          const int ntap = src == 0 ? 27 : 1;
-          for (int pass = 0; pass < p.npass; ++pass) {
-            {
-              const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
-              mbar_wait(&halo_empty[s], ph ^ 1);
-              mbar_expect_tx_if(issue, &halo_full[s], Cfg::HALO_TX);
-              const int hrows = 18 / hp.hsplit;
-              for (int dp = 0; dp < TD + 2; ++dp)
-                for (int hq = 0; hq < hp.hsplit; ++hq)
-                  tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES + ((dp * 18 + hq * hrows) * 10) * Cfg::RB,
-                                 &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1, h0 - 1 + hq * hrows, d0 - 1 + dp, n);
-              ++hi;
-            }
-            for (int tap = 0; tap < ntap; ++tap) {
-              const uint32_t s = bi % Cfg::NB, ph = (bi / Cfg::NB) & 1;
-              mbar_wait(&b_empty[s], ph ^ 1);
-              mbar_expect_tx_if(issue, &b_full[s], Cfg::B_TX);
-              tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, tap);
-              ++bi;
-            }
+    const uint32_t issue = elect_one() ? 1u : 0u;
+    uint32_t hi = 0, bi = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int nt = t % hp.ntiles; t /= hp.ntiles;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int dt = t % p.tiles_d;
+      const int n = t / p.tiles_d;
+      const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
+      HALO_STAMP(0, 0);
+      for (int g = 0; g < groups0 + groups1; ++g) {
+        const int src = g < groups0 ? 0 : 1;
+        const int kc = src == 0 ? g : g - groups0;
+        const int nstage = src == 0 ? STAGES0 : 1;
+        for (int pass = 0; pass < p.npass; ++pass) {
+          {
+            const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
+            mbar_wait(&halo_empty[s], ph ^ 1);
+            HALO_STAMP(0, 1);
+            mbar_expect_tx_if(issue, &halo_full[s], Cfg::HALO_TX);
+            const int hrows = 18 / hp.hsplit;
+            for (int dp = 0; dp < TD + 2; ++dp)
+              for (int hq = 0; hq < hp.hsplit; ++hq)
+                tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES + ((dp * 18 + hq * hrows) * 10) * Cfg::RB,
+                               &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1, h0 - 1 + hq * hrows, d0 - 1 + dp, n);
+            ++hi;
+          }
+          for (int st = 0; st < nstage; ++st) {
+            const uint32_t s = bi % NB, ph = (bi / NB) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx_if(issue, &b_full[s], src == 0 ? Cfg::B_TX : Cfg::B_TAP);
+            tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0,
+                           src == 0 ? st * Cfg::TPB : 0);
+            ++bi;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-convergent, one lane issues)
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT);
-      constexpr uint32_t hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT);
-      const uint32_t issue = elect_one() ? 1u : 0u;
-      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t halo0 = smem_u32(smem_halo), b0 = smem_u32(smem_b);
-      uint32_t hi = 0, bi = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
-        const uint32_t as = ti % Cfg::NACC;
-        mbar_wait(&acc_empty[as], ((ti / Cfg::NACC) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t acc0 = tmem0 + as * TD * BN;
-        uint32_t first = 1;
-        for (int g = 0; g < groups0 + groups1; ++g) {
-          const int src = g < groups0 ? 0 : 1;
-          const int ntap = src == 0 ? 27 : 1;
-          for (int pass = 0; pass < p.npass; ++pass) {
-            const uint32_t hs = hi % Cfg::NHALO;
-            mbar_wait(&halo_full[hs], (hi / Cfg::NHALO) & 1);
-            const uint32_t halo_lo = desc_lo(halo0 + hs * Cfg::HALO_BYTES, 16);
-            for (int tap = 0; tap < ntap; ++tap) {
-              const int tt = src == 0 ? tap : 13;
+    // ------------------------------------------------------------------ MMA issuer (convergent, one lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT);
+    constexpr uint32_t hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT);
+    const uint32_t issue = elect_one() ? 1u : 0u;
+    const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t halo0 = smem_u32(smem_halo), b0 = smem_u32(smem_b);
+    uint32_t hi = 0, bi = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
+      const uint32_t as = ti % Cfg::NACC;
+      HALO_STAMP(1, 0);
+      mbar_wait(&acc_empty[as], ((ti / Cfg::NACC) & 1) ^ 1);
+      tc_fence_after();
+      HALO_STAMP(1, 1);
+      const uint32_t acc0 = tmem0 + as * TD * BN;
+      uint32_t first = 1;
+      for (int g = 0; g < groups0 + groups1; ++g) {
+        const int src = g < groups0 ? 0 : 1;
+        const int nstage = src == 0 ? STAGES0 : 1;
+        for (int pass = 0; pass < p.npass; ++pass) {
+          const uint32_t hs = hi % Cfg::NHALO;
+          mbar_wait(&halo_full[hs], (hi / Cfg::NHALO) & 1);
+          HALO_STAMP(1, 2);
+          const uint32_t halo_lo = desc_lo(halo0 + hs * Cfg::HALO_BYTES, 16);
+          for (int st = 0; st < nstage; ++st) {
+            const uint32_t bs = bi % NB;
+            mbar_wait(&b_full[bs], (bi / NB) & 1);
+            tc_fence_after();
+            const uint32_t b_lo0 = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
+#pragma unroll
+            for (int tp = 0; tp < Cfg::TPB; ++tp) {
+              if (src == 1 && tp > 0) break;
+              const int tt = src == 0 ? st * Cfg::TPB + tp : 13;
               const int kd = tt / 9, kh = (tt / 3) % 3, kw = tt % 3;
-              const uint32_t bs = bi % Cfg::NB;
-              mbar_wait(&b_full[bs], (bi / Cfg::NB) & 1);
-              tc_fence_after();
-              const uint32_t b_lo = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
               const uint32_t a_lo = halo_lo + (((kd * 18 + kh) * 10 + kw) * Cfg::RB >> 4);
+              const uint32_t b_lo = b_lo0 + (tp * Cfg::B_TAP >> 4);
 #pragma unroll
               for (int dpl = 0; dpl < TD; ++dpl) {
 #pragma unroll
@@ -174,23 +201,20 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
                 }
               }
               first = 0;
-              umma_commit_if(issue, &b_empty[bs]);
-              ++bi;
             }
-            umma_commit_if(issue, &halo_empty[hs]);
-            ++hi;
+            umma_commit_if(issue, &b_empty[bs]);
+            ++bi;
           }
+          umma_commit_if(issue, &halo_empty[hs]);
+          ++hi;
         }
-        umma_commit_if(issue, &acc_full[as]);
       }
+      umma_commit_if(issue, &acc_full[as]);
+      HALO_STAMP(1, 3);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Loop order: 16-column chunk outer, the tile's TD planes inner, so the per-channel statistics are accumulated
-    // in registers over planes (BN >= 64: one butterfly reduction per chunk per tile) or over planes AND tiles
-    // (BN <= 32: "running" sums, reduced only when the sample / channel tile changes and at the end).  The
-    // butterflies were the bottleneck of the narrow layers (ncu: profiles/r01_halo_epilogue.txt).
-    constexpr bool RUN = (BN <= 32);
+    constexpr bool RUN = Cfg::RUN;
     constexpr int NCH = BN / 16;
     constexpr int NACCUM = RUN ? BN : 16;
     const int lane_base = (warp & 3) * 32;
@@ -202,15 +226,16 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
     const int side_ld = p.mode == 0 ? p.ldr : p.ldx;
     double* stat_dst = (p.mode == 0) ? p.stats : p.bstats;
     const int stat_ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
+    const bool split = hp.split != 0;
     float rs[NACCUM], rq[NACCUM];
 #pragma unroll
     for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    uint32_t ti = 0;
+    uint32_t ti = 0, oi = 0;   // tile counter, output-plane counter (staging ring)
     int cur_n = -1, cur_n0 = -1;
 
-    // s_stats (already holding every warp's partial sums) -> global fp64 atomics, then re-zero
+    // s_stats (holding every warp's partial sums) -> global fp64 atomics, then re-zero
     auto flush_smem = [&](int fn, int fn0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = e; c < BN; c += 128) {
@@ -222,6 +247,18 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
         s_stats[c * 2 + 1] = 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    // register accumulators of chunk j -> transposing butterfly -> s_stats
+    auto reduce_chunk = [&](int j, const float* sv, const float* sq) {
+      float v16[16], q16[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { v16[i] = sv[i]; q16[i] = sq[i]; }
+      const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
+      if ((lane & 1) == 0) {
+        const int col = j * 16 + ((lane >> 1) & 15);
+        atomicAdd(&s_stats[col * 2 + 0], s1);
+        atomicAdd(&s_stats[col * 2 + 1], s2);
+      }
     };
 
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
@@ -235,17 +272,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       if (n != cur_n || n0 != cur_n0) {
         if (RUN && want_stats && cur_n >= 0) {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) {
-            float v16[16], q16[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { v16[i] = rs[(RUN ? j * 16 : 0) + i]; q16[i] = rq[(RUN ? j * 16 : 0) + i]; }
-            const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
-            if ((lane & 1) == 0) {
-              const int col = j * 16 + ((lane >> 1) & 15);
-              atomicAdd(&s_stats[col * 2 + 0], s1);
-              atomicAdd(&s_stats[col * 2 + 1], s2);
-            }
-          }
+          for (int j = 0; j < NCH; ++j) reduce_chunk(j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
 #pragma unroll
           for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
           flush_smem(cur_n, cur_n0);
@@ -266,50 +293,56 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       for (int dpl = 0; dpl < TD; ++dpl)     // side-input rows of this tile -> L2 while the MMAs are still running
         conv_epilogue_prefetch(p, n0, BN, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
       const uint32_t as = ti % Cfg::NACC;
+      if (warp == 2) HALO_STAMP(2, 0);
       mbar_wait(&acc_full[as], (ti / Cfg::NACC) & 1);
       tc_fence_after();
+      if (warp == 2) HALO_STAMP(2, 1);
+#pragma unroll 1
+      for (int dpl = 0; dpl < TD; ++dpl, ++oi) {
+        const int d = d0 + dpl;
+        const bool valid = valid_wh && (d < p.Do);
+        const long long vox = vox0 + dpl * plane;
+        uint8_t* stage = smem_out + (oi % hp.nout) * out_buf_bytes;
+        // side input (residual / norm input) of this row for all chunks of the plane: one latency per plane
+        uint4 sh[2 * NCH], sl[2 * NCH];
+        if (side_hi && valid) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const int c0 = n0 + j * 16;
-        if (c0 < p.Cout) {
-          // side input (residual / norm input) of this chunk for all planes: one latency for TD planes
-          uint4 sh[TD][2], sl[TD][2];
-          if (side_hi) {
-#pragma unroll
-            for (int dpl = 0; dpl < TD; ++dpl) {
-              if (valid_wh && (d0 + dpl < p.Do)) {
-                const long long off = (vox0 + dpl * plane) * side_ld + c0;
-                sh[dpl][0] = *reinterpret_cast<const uint4*>(side_hi + off);
-                if (c0 + 8 < p.Cout) sh[dpl][1] = *reinterpret_cast<const uint4*>(side_hi + off + 8);
-                if (side_lo) {
-                  sl[dpl][0] = *reinterpret_cast<const uint4*>(side_lo + off);
-                  if (c0 + 8 < p.Cout) sl[dpl][1] = *reinterpret_cast<const uint4*>(side_lo + off + 8);
-                }
-              }
+          for (int c = 0; c < 2 * NCH; ++c) {
+            if (n0 + c * 8 < p.Cout) {
+              sh[c] = *reinterpret_cast<const uint4*>(side_hi + vox * side_ld + n0 + c * 8);
+              if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vox * side_ld + n0 + c * 8);
             }
           }
+        }
+        if (hp.nout == 1) {   // single staging buffer: the previous plane's store must have finished reading it
+          if (threadIdx.x == 64) tma_store_wait_read0();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int c0 = n0 + j * 16;
           float* as_ = rs + (RUN ? j * 16 : 0);
           float* aq_ = rq + (RUN ? j * 16 : 0);
-#pragma unroll
-          for (int dpl = 0; dpl < TD; ++dpl) {
-            const bool valid = valid_wh && (d0 + dpl < p.Do);
-            const long long vox = vox0 + dpl * plane;
+          if (c0 < p.Cout) {
             uint32_t r[16];
             tmem_ld16(tmem_base + (as * TD + dpl) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
             tmem_ld_wait();
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const int cc = c0 + hf * 8;
+              float vv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = 0.f;
               if (cc < p.Cout && valid) {
-                float vv[8], sv[8];
+                float sv[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[hf * 8 + i]);
                 if (side_hi) {
-                  const uint4 a = sh[dpl][hf];
+                  const uint4 a = sh[j * 2 + hf];
                   sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
                   sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
                   if (side_lo) {
-                    const uint4 b = sl[dpl][hf];
+                    const uint4 b = sl[j * 2 + hf];
                     sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
                     sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);
                   }
@@ -327,7 +360,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
 #pragma unroll
                     for (int i = 0; i < 8; ++i) vv[i] += __ldg(p.bias + cc + i);
                   }
-                  if (p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d0 + dpl == p.Do - 1)) {
+                  if (p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d == p.Do - 1)) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) vv[i] = 0.f;
                   }
@@ -344,64 +377,83 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
                     aq_[hf * 8 + i] = fmaf(dz, (sv[i] - k.z) * k.w, aq_[hf * 8 + i]);
                   }
                 }
-                epi_store8(p.out_hi, p.out_lo, vox * p.ldo + cc, vv);
+              }
+              // stage the 8 channels (16 bytes) of this row: box (cc - n0) / CBO, chunk within the box row
+              uint4 o;
+              o.x = pack_bf16x2(vv[0], vv[1]); o.y = pack_bf16x2(vv[2], vv[3]);
+              o.z = pack_bf16x2(vv[4], vv[5]); o.w = pack_bf16x2(vv[6], vv[7]);
+              const int cb = (j * 16 + hf * 8) / Cfg::CBO, cchunk = ((j * 16 + hf * 8) % Cfg::CBO) / 8;
+              uint8_t* dst = stage + cb * Cfg::OUT_BOX + stage_off<Cfg::CBO>(row, cchunk);
+              *reinterpret_cast<uint4*>(dst) = o;
+              if (split) {
+                uint4 l;
+                l.x = pack_bf16x2(vv[0] - bf16_lo_to_f(o.x), vv[1] - bf16_hi_to_f(o.x));
+                l.y = pack_bf16x2(vv[2] - bf16_lo_to_f(o.y), vv[3] - bf16_hi_to_f(o.y));
+                l.z = pack_bf16x2(vv[4] - bf16_lo_to_f(o.z), vv[5] - bf16_hi_to_f(o.z));
+                l.w = pack_bf16x2(vv[6] - bf16_lo_to_f(o.w), vv[7] - bf16_hi_to_f(o.w));
+                *reinterpret_cast<uint4*>(dst + Cfg::OUT_TILE) = l;
               }
             }
-          }
-          if constexpr (!RUN) {
-            if (want_stats) {
-              float v16[16], q16[16];
+            if constexpr (!RUN) {
+              if (want_stats) reduce_chunk(j, rs, rq);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { v16[i] = rs[i]; q16[i] = rq[i]; }
-              const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
-              if ((lane & 1) == 0) {
-                const int col = j * 16 + ((lane >> 1) & 15);
-                atomicAdd(&s_stats[col * 2 + 0], s1);
-                atomicAdd(&s_stats[col * 2 + 1], s2);
-              }
+              for (int i = 0; i < 16; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
           }
+        }
+        // the plane is staged: make it visible to the async proxy, then one thread TMA-stores it
+        fence_proxy_async();
+        if (hp.nout > 1 && threadIdx.x == 64) tma_store_wait_read0();   // the other buffer is free again after the barrier
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64 && d < p.Do) {
+#pragma unroll
+          for (int cb = 0; cb < Cfg::NBO; ++cb) {
+            if (n0 + cb * Cfg::CBO < p.Cout) {
+              tma_store_5d(&maps.o[0], stage + cb * Cfg::OUT_BOX, n0 + cb * Cfg::CBO, w0, h0, d, n);
+              if (split) tma_store_5d(&maps.o[1], stage + Cfg::OUT_TILE + cb * Cfg::OUT_BOX, n0 + cb * Cfg::CBO, w0, h0, d, n);
+            }
+          }
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);      // accumulator set drained: MMA may overwrite it
+      if (warp == 2) HALO_STAMP(2, 2);
       if (!RUN && want_stats) flush_smem(n, n0);
+      if (warp == 2) HALO_STAMP(2, 3);
     }
     if (RUN && want_stats && cur_n >= 0) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        float v16[16], q16[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { v16[i] = rs[(RUN ? j * 16 : 0) + i]; q16[i] = rq[(RUN ? j * 16 : 0) + i]; }
-        const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
-        if ((lane & 1) == 0) {
-          const int col = j * 16 + ((lane >> 1) & 15);
-          atomicAdd(&s_stats[col * 2 + 0], s1);
-          atomicAdd(&s_stats[col * 2 + 1], s2);
-        }
-      }
+      for (int j = 0; j < NCH; ++j) reduce_chunk(j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
       flush_smem(cur_n, cur_n0);
     }
+    if (threadIdx.x == 64) tma_store_wait_all();       // all output tiles have left shared memory and are written
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 template <int KC, int BN, int TD>
-static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, const HaloArgs& h, int grid, cudaStream_t st) {
+static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, int grid, cudaStream_t st) {
   using Cfg = HaloCfg<KC, BN, TD>;
+  // shared-memory carve-up: 2 halo buffers | nout output staging buffers | weight ring | aux
+  const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
+  const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
+  h.nout = (rem - 2 * out_buf >= 4 * Cfg::B_BYTES) ? 2 : 1;
+  int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
+  if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
+  B200_REQUIRE(nb >= 2, E_UNSUPPORTED, "conv_halo: configuration KC=%d BN=%d TD=%d does not fit shared memory", KC, BN, TD);
+  h.nb = nb;
+  const int smem_bytes = Cfg::NHALO * Cfg::HALO_BYTES + h.nout * out_buf + nb * Cfg::B_BYTES + Cfg::AUX_BYTES + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a, h);
+  k_conv_halo<KC, BN, TD><<<grid, 192, smem_bytes, st>>>(maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -414,6 +466,16 @@ bool conv_halo_eligible(const ConvOp& op) {
   if (op.src[0].ksz != 3 || op.src[0].stride != 1) return false;
   if (op.nsrc == 2 && (op.src[1].ksz != 1 || op.src[1].stride != 1)) return false;
   return op.out.W >= 8 && op.out.H >= 16;
+}
+
+// does (KC, BN, TD, split) fit the shared-memory budget with at least a 2-deep weight ring and 1 staging buffer?
+static bool halo_fits(int KC, int BN, int TD, bool split) {
+  const int halo = (180 * (TD + 2) * KC * 2 + 1023) / 1024 * 1024;
+  const int tpb = BN <= 64 ? 3 : 1;
+  const int bbytes = (tpb * BN * KC * 2 + 1023) / 1024 * 1024;
+  const int aux = 1024 + BN * 8 + BN * 16;
+  const int out_buf = 128 * BN * 2 * (split ? 2 : 1);
+  return 232448 - 1024 - aux - 2 * halo - out_buf >= 2 * bbytes;
 }
 
 int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
@@ -435,9 +497,11 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     if (c.x.C > cin_max) cin_max = c.x.C;
     if (c.x.lo || c.w_lo) split = true;
   }
-  if (split)
+  if (split) {
     for (int s = 0; s < op.nsrc; ++s)
       B200_REQUIRE(op.src[s].x.lo && op.src[s].w_lo, E_INVALID, "conv_halo: split mode needs lo parts on every source");
+    B200_REQUIRE(out.lo != nullptr, E_INVALID, "conv_halo: split mode needs a lo output");
+  }
   const int KC = cin_max > 16 ? 32 : 16;
   int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
   if (const char* e = getenv("B200UNET_HALO_BN")) {   // tuning override: cap the N tile
@@ -445,14 +509,15 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     if ((v == 16 || v == 32 || v == 64 || v == 128) && v < BN) BN = v;
   }
   const int ntiles = ceil_div(out.C, BN);
-  // TD: deepest tile that still gives every SM work (>= ~2 tiles per SM), bounded by TMEM (TD*BN <= 512)
+  // TD: deepest tile that still gives every SM work (>= ~2 tiles per SM), bounded by TMEM (TD*BN <= 512) and smem
   int TD = 4;
   auto tiles_for = [&](int td) { return (long long)out.N * ceil_div(out.D, td) * ceil_div(out.H, 16) * ceil_div(out.W, 8) * ntiles; };
-  while (TD > 1 && (tiles_for(TD) < 2LL * num_sms || out.D < TD)) TD >>= 1;
+  while (TD > 1 && (tiles_for(TD) < 2LL * num_sms || out.D < TD || !halo_fits(KC, BN, TD, split))) TD >>= 1;
   if (const char* e = getenv("B200UNET_HALO_TD")) {   // tuning override (1, 2 or 4)
     const int v = atoi(e);
-    if ((v == 1 || v == 2 || v == 4) && v * BN <= 512) TD = v;
+    if ((v == 1 || v == 2 || v == 4) && v * BN <= 512 && halo_fits(KC, BN, v, split)) TD = v;
   }
+  B200_REQUIRE(halo_fits(KC, BN, TD, split), E_UNSUPPORTED, "conv_halo: KC=%d BN=%d does not fit shared memory", KC, BN);
   a.tw = 8; a.th = 16; a.td = TD;
   a.tiles_w = ceil_div(out.W, 8); a.tiles_h = ceil_div(out.H, 16); a.tiles_d = ceil_div(out.D, TD);
   const Swz swz = swz_for_bytes(KC * 2);
@@ -462,17 +527,26 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     const int v = atoi(e);
     if ((v == 1 || v == 2 || v == 3 || v == 6) && ((18 / v) * 10 * KC * 2) % 128 == 0) hsplit = v;
   }
+  const int tpb = BN <= 64 ? 3 : 1;
   for (int s = 0; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = 1;
     a.kchunks[s] = ceil_div(c.x.C, KC);
-    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz, c.x.vD, c.x.vH, c.x.vW));
-    B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+    const int boxT = (s == 0) ? tpb : 1;
+    B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz,
+                          c.x.vD, c.x.vH, c.x.vW));
+    B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
     if (split) {
-      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz, c.x.vD, c.x.vH, c.x.vW));
-      B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
+      B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz,
+                            c.x.vD, c.x.vH, c.x.vW));
+      B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
     }
   }
+  // output tile stores: box (min(BN,64) channels, 8, 16, 1, 1), swizzle by the box row bytes
+  const int cbo = BN < 64 ? BN : 64;
+  B200_TRY(make_act_map(&maps.o[0], out.hi, out.N, out.D, out.H, out.W, out.C, out.ld, cbo, 8, 16, 1, 1, swz_for_bytes(cbo * 2)));
+  if (split)
+    B200_TRY(make_act_map(&maps.o[1], out.lo, out.N, out.D, out.H, out.W, out.C, out.ld, cbo, 8, 16, 1, 1, swz_for_bytes(cbo * 2)));
   a.npass = split ? 3 : 1;
   a.mode = op.mode;
   a.out_hi = out.hi; a.out_lo = out.lo; a.ldo = out.ld;
@@ -491,8 +565,12 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     a.slope = op.slope; a.bstats = op.bstats;
   }
   HaloArgs h;
+  memset(&h, 0, sizeof(h));
   h.ntiles = ntiles;
   h.hsplit = hsplit;
+  h.split = split ? 1 : 0;
+  h.dbg = nullptr;
+  if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);
   const int grid = h.tiles_total < num_sms ? h.tiles_total : num_sms;
 #define B200_HALO_CASE(kc, bn, td) \

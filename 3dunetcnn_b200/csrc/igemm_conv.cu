@@ -33,7 +33,9 @@ struct ConvCfg {
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;  // barriers+slot | stats | coef
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int OUT_STAGING = 2 * 128 * BN * 2;    // hi + lo output tiles, aliased onto the pipeline stages
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES > OUT_STAGING ? STAGES * STAGE_BYTES : OUT_STAGING;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + AUX_BYTES + 1024;  // +1024 alignment slack
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO = 8 * KC * 2;
 };
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   using Cfg = ConvCfg<BN, KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* aux = smem + Cfg::PIPE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
@@ -155,9 +157,24 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     tc_fence_after();
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
     const bool edge = p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d == p.Do - 1);
-    conv_epilogue_tile<BN>(p, tmem_base, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge);
+    // all MMAs have completed (tfull) => every pipeline stage has been consumed: the stage memory is free and is reused
+    // as the output staging tile [BN/CBO boxes][128 rows][CBO] (+ lo tile), TMA-stored below
+    const bool split = p.out_lo != nullptr;
+    conv_epilogue_tile<BN>(p, tmem_base, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, row, split);
+    fence_proxy_async();
     tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      constexpr int CBO = BN < 64 ? BN : 64;
+#pragma unroll
+      for (int cb = 0; cb < BN / CBO; ++cb) {
+        if (n0 + cb * CBO < p.Cout) {
+          tma_store_5d(&maps.o[0], smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+          if (split) tma_store_5d(&maps.o[1], smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+        }
+      }
+      tma_store_commit();
+    }
     if (want_stats) {
       const int e = threadIdx.x - 64;
       double* dst = (p.mode == 0) ? p.stats : p.bstats;
@@ -169,6 +186,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
         }
       }
     }
+    if (threadIdx.x == 64) tma_store_wait_all();   // the staging tile must outlive the bulk store
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -268,6 +286,15 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
   a.npass = split ? 3 : 1;
   a.mode = op.mode;
   a.out_hi = out.hi; a.out_lo = out.lo; a.ldo = out.ld;
+  if (split) B200_REQUIRE(out.lo != nullptr, E_INVALID, "igemm_conv: split mode needs a lo output");
+  {
+    const int cbo = BN < 64 ? BN : 64;
+    B200_TRY(make_act_map(&maps.o[0], out.hi, out.N, out.D, out.H, out.W, out.C, out.ld, cbo, a.tw, a.th, a.td, 1,
+                          swz_for_bytes(cbo * 2)));
+    if (split)
+      B200_TRY(make_act_map(&maps.o[1], out.lo, out.N, out.D, out.H, out.W, out.C, out.ld, cbo, a.tw, a.th, a.td, 1,
+                            swz_for_bytes(cbo * 2)));
+  }
   if (op.res) {
     B200_REQUIRE(op.res->C == out.C, E_INVALID, "igemm_conv: residual channel mismatch");
     a.res_hi = op.res->hi; a.res_lo = op.res->lo; a.ldr = op.res->ld;

@@ -51,14 +51,14 @@ int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, 
   return OK;
 }
 
-int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz) {
+int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz, int boxT) {
   EncodeTiledFn enc = get_encode();
   B200_REQUIRE(enc != nullptr, E_DRIVER, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, E_INVALID, "weight pointer not 16B aligned");
   B200_REQUIRE((K * 2) % 16 == 0, E_INVALID, "packed weight K=%d not a multiple of 8", K);
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)T};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)R * K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)boxK, (cuuint32_t)boxR, 1};
+  cuuint32_t box[3] = {(cuuint32_t)boxK, (cuuint32_t)boxR, (cuuint32_t)boxT};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, to_cu(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
