@@ -161,4 +161,11 @@ int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stre
   return launch_umma_probe(tests, ntests, out, to_stream(stream));
 }
 
+int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
+                       void* stream) {
+  NOT_NULL(out);
+  return launch_umma_rate(n, layout, a_sbo, b_sbo, a_step, inner, reps, ctas, reinterpret_cast<long long*>(out),
+                          to_stream(stream));
+}
+
 }  // extern "C"

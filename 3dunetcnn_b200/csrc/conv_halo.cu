@@ -46,7 +46,7 @@ struct HaloCfg {
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
   static constexpr uint32_t SBO_B = 8 * RB;
-  static constexpr bool RUN = BN <= 64;                     // register-resident running statistics
+  static constexpr bool RUN = BN <= 32;                     // register-resident running statistics
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
   static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
 };
@@ -60,11 +60,13 @@ struct HaloArgs {
   int split;
   long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
+#define EPI_STAMP(idx) \
+  do { if (hp.dbg && blockIdx.x == 0 && ti == 4 && warp == 2 && lane == 0) hp.dbg[384 + (idx)] = clock64(); } while (0)
 #define HALO_STAMP(role, slot) \
   do { if (hp.dbg && blockIdx.x == 0 && ti < 32 && lane == 0) hp.dbg[((role) * 32 + ti) * 4 + (slot)] = clock64(); } while (0)
 
 template <int KC, int BN, int TD>
-__global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
+__global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
                                                       const HaloArgs hp) {
   using Cfg = HaloCfg<KC, BN, TD>;
   extern __shared__ uint8_t smem_raw[];
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
     if (lane == 0) {
       for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
       for (int s = 0; s < Cfg::NB_MAX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-      for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+      for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -214,12 +216,19 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // 8 warps in two groups of 4 (one warp per TMEM lane quadrant in each group): group g drains the planes
+    // dpl = g, g+2, ... of every tile into its own staging buffers, so two planes are in flight per SM and every
+    // scheduler interleaves two epilogue warps (a single warp per scheduler ran latency-bound at ~600 cycles per
+    // 16-column chunk: profiles/r01_halo_timeline.txt).
     constexpr bool RUN = Cfg::RUN;
     constexpr int NCH = BN / 16;
     constexpr int NACCUM = RUN ? BN : 16;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
-    const int e = threadIdx.x - 64;
+    const int e = threadIdx.x - 64;           // 0..255
+    const int grp = (warp - 2) >> 2;          // plane-parity group
+    const int issuer = 64 + grp * 128;        // the thread of this group that issues its TMA stores
+    const int nog = hp.nout >> 1;             // staging buffers per group (1 or 2)
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
     const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
     const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
@@ -230,15 +239,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
     float rs[NACCUM], rq[NACCUM];
 #pragma unroll
     for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
-    for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = e; i < BN * 2; i += 256) s_stats[i] = 0.f;
+    asm volatile("bar.sync 3, 256;" ::: "memory");
     uint32_t ti = 0, oi = 0;   // tile counter, output-plane counter (staging ring)
     int cur_n = -1, cur_n0 = -1;
 
     // s_stats (holding every warp's partial sums) -> global fp64 atomics, then re-zero
     auto flush_smem = [&](int fn, int fn0) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = e; c < BN; c += 128) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int c = e; c < BN; c += 256) {
         if (fn0 + c < p.Cout) {
           atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
           atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
         s_stats[c * 2 + 0] = 0.f;
         s_stats[c * 2 + 1] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 3, 256;" ::: "memory");
     };
     // register accumulators of chunk j -> transposing butterfly -> s_stats
     auto reduce_chunk = [&](int j, const float* sv, const float* sq) {
@@ -278,10 +287,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
           flush_smem(cur_n, cur_n0);
         }
         if (p.mode == 1) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");   // nobody still reads the old coefficients
-          for (int c = e; c < BN; c += 128)
+          asm volatile("bar.sync 3, 256;" ::: "memory");   // nobody still reads the old coefficients
+          for (int c = e; c < BN; c += 256)
             s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 3, 256;" ::: "memory");
         }
         cur_n = n; cur_n0 = n0;
       }
@@ -289,8 +298,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       const bool valid_wh = (w < p.Wo) && (h < p.Ho);
       const long long vox0 = (((long long)n * p.Do + d0) * p.Ho + h) * p.Wo + w;   // plane dpl: + dpl * Ho * Wo
       const long long plane = (long long)p.Ho * p.Wo;
-#pragma unroll
-      for (int dpl = 0; dpl < TD; ++dpl)     // side-input rows of this tile -> L2 while the MMAs are still running
+      for (int dpl = grp; dpl < TD; dpl += 2)     // side-input rows of this group's planes -> L2 while the MMAs still run
         conv_epilogue_prefetch(p, n0, BN, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
       const uint32_t as = ti % Cfg::NACC;
       if (warp == 2) HALO_STAMP(2, 0);
@@ -298,31 +306,34 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       tc_fence_after();
       if (warp == 2) HALO_STAMP(2, 1);
 #pragma unroll 1
-      for (int dpl = 0; dpl < TD; ++dpl, ++oi) {
+      for (int dpl = grp; dpl < TD; dpl += 2, ++oi) {
         const int d = d0 + dpl;
         const bool valid = valid_wh && (d < p.Do);
         const long long vox = vox0 + dpl * plane;
-        uint8_t* stage = smem_out + (oi % hp.nout) * out_buf_bytes;
-        // side input (residual / norm input) of this row for all chunks of the plane: one latency per plane
-        uint4 sh[2 * NCH], sl[2 * NCH];
-        if (side_hi && valid) {
-#pragma unroll
-          for (int c = 0; c < 2 * NCH; ++c) {
-            if (n0 + c * 8 < p.Cout) {
-              sh[c] = *reinterpret_cast<const uint4*>(side_hi + vox * side_ld + n0 + c * 8);
-              if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vox * side_ld + n0 + c * 8);
-            }
-          }
-        }
-        if (hp.nout == 1) {   // single staging buffer: the previous plane's store must have finished reading it
-          if (threadIdx.x == 64) tma_store_wait_read0();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* stage = smem_out + (grp * nog + (oi % nog)) * out_buf_bytes;
+        EPI_STAMP(dpl * 8 + 0);
+        // side input (residual / norm input): preloaded for groups of two 16-column chunks (one latency per 32 columns)
+        constexpr int SG = NCH < 2 ? NCH : 2;
+        uint4 sh[2 * SG], sl[2 * SG];
+        if (nog == 1) {   // single staging buffer per group: its previous store must have finished reading it
+          if (threadIdx.x == issuer) tma_store_wait_read0();
+          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
         }
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
           const int c0 = n0 + j * 16;
           float* as_ = rs + (RUN ? j * 16 : 0);
           float* aq_ = rq + (RUN ? j * 16 : 0);
+          if ((j % SG) == 0 && side_hi && valid) {
+#pragma unroll
+            for (int c = 0; c < 2 * SG; ++c) {
+              if (c0 + c * 8 < p.Cout) {
+                sh[c] = *reinterpret_cast<const uint4*>(side_hi + vox * side_ld + c0 + c * 8);
+                if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vox * side_ld + c0 + c * 8);
+              }
+            }
+          }
           if (c0 < p.Cout) {
             uint32_t r[16];
             tmem_ld16(tmem_base + (as * TD + dpl) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
@@ -338,11 +349,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[hf * 8 + i]);
                 if (side_hi) {
-                  const uint4 a = sh[j * 2 + hf];
+                  const uint4 a = sh[(j % SG) * 2 + hf];
                   sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
                   sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
                   if (side_lo) {
-                    const uint4 b = sl[j * 2 + hf];
+                    const uint4 b = sl[(j % SG) * 2 + hf];
                     sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
                     sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);
                   }
@@ -402,10 +413,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
           }
         }
         // the plane is staged: make it visible to the async proxy, then one thread TMA-stores it
+        EPI_STAMP(dpl * 8 + 2);
         fence_proxy_async();
-        if (hp.nout > 1 && threadIdx.x == 64) tma_store_wait_read0();   // the other buffer is free again after the barrier
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64 && d < p.Do) {
+        EPI_STAMP(dpl * 8 + 3);
+        if (nog > 1 && threadIdx.x == issuer) tma_store_wait_read0();   // the other buffer is free again after the barrier
+        EPI_STAMP(dpl * 8 + 4);
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        EPI_STAMP(dpl * 8 + 5);
+        if (threadIdx.x == issuer && d < p.Do) {
 #pragma unroll
           for (int cb = 0; cb < Cfg::NBO; ++cb) {
             if (n0 + cb * Cfg::CBO < p.Cout) {
@@ -415,6 +431,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
           }
           tma_store_commit();
         }
+        EPI_STAMP(dpl * 8 + 6);
       }
       tc_fence_before();
       __syncwarp();
@@ -428,7 +445,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ Co
       for (int j = 0; j < NCH; ++j) reduce_chunk(j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
       flush_smem(cur_n, cur_n0);
     }
-    if (threadIdx.x == 64) tma_store_wait_all();       // all output tiles have left shared memory and are written
+    if (threadIdx.x == issuer) tma_store_wait_all();   // all output tiles have left shared memory and are written
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -440,7 +457,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   // shared-memory carve-up: 2 halo buffers | nout output staging buffers | weight ring | aux
   const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
-  h.nout = (rem - 2 * out_buf >= 4 * Cfg::B_BYTES) ? 2 : 1;
+  h.nout = (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;   // staging buffers: 2 per plane-parity group if they fit
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
   B200_REQUIRE(nb >= 2, E_UNSUPPORTED, "conv_halo: configuration KC=%d BN=%d TD=%d does not fit shared memory", KC, BN, TD);
@@ -453,7 +470,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
     B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD><<<grid, 192, smem_bytes, st>>>(maps, a, h);
+  k_conv_halo<KC, BN, TD><<<grid, 320, smem_bytes, st>>>(maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -475,7 +492,7 @@ static bool halo_fits(int KC, int BN, int TD, bool split) {
   const int bbytes = (tpb * BN * KC * 2 + 1023) / 1024 * 1024;
   const int aux = 1024 + BN * 8 + BN * 16;
   const int out_buf = 128 * BN * 2 * (split ? 2 : 1);
-  return 232448 - 1024 - aux - 2 * halo - out_buf >= 2 * bbytes;
+  return 232448 - 1024 - aux - 2 * halo - 2 * out_buf >= 2 * bbytes;
 }
 
 int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {

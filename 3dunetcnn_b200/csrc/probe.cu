@@ -71,6 +71,59 @@ __global__ void __launch_bounds__(128) k_umma_probe(int layout_mode, int start_o
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+// ---- MMA issue-rate micro-benchmark: one warp per CTA issues `reps` x `inner` tcgen05.mma (M=128, N, K=16, bf16)
+// on resident (zeroed) shared-memory operands and reports clock64 cycles per MMA.  a_sbo / layout / a_step let the
+// caller mimic the halo kernel's shifted, re-strided A descriptors.
+__global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps,
+                                                  long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 160 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (warp == 0) {
+    const uint32_t issue = elect_one() ? 1u : 0u;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t hi_a = desc_hi(a_sbo, layout), hi_b = desc_hi(b_sbo, layout);
+    const uint32_t a_lo = desc_lo(smem_u32(smem), 16), b_lo = desc_lo(smem_u32(smem + 96 * 1024), 16);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll 4
+      for (int i = 0; i < inner; ++i)
+        umma_bf16_if(issue, tm + (i & 1) * 256, desc_from(a_lo + ((i * a_step) >> 4), hi_a), desc_from(b_lo + ((i & 3) * 2), hi_b),
+                     idesc, 1u);
+    }
+    umma_commit_if(issue, bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int launch_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, long long* out,
+                     cudaStream_t st) {
+  const int smem = 160 * 1024 + 64 + 1024;
+  B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
 int launch_umma_probe(const int* tests, int ntests, float* out, cudaStream_t st) {
   const int smem = 65536 + 8192 + 64 + 1024;
   B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

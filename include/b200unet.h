@@ -166,6 +166,9 @@ int b200unet_plan_profile_dump(b200unet_plan* plan, const char* path);
 
 /* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
 int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
+/* tcgen05.mma issue-rate micro-benchmark (M=128, N=n, K=16): cycles for reps*inner MMAs per CTA -> out[cta] */
+int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
+                       void* stream);
 
 #ifdef __cplusplus
 }

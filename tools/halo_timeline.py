@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 ci, co, r = [int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (32, 32, 128))]
 mode = sys.argv[4] if len(sys.argv) > 4 else "plain"
-dbg = torch.zeros(3 * 32 * 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(3 * 32 * 4 + 64, dtype=torch.int64, device="cuda")
 os.environ["B200UNET_HALO_DBG"] = str(dbg.data_ptr())
 pkg = importlib.import_module("3dunetcnn_b200")
 L = pkg.lib
@@ -29,7 +29,8 @@ if mode == "mode1":
 for _ in range(3):
     L.conv3d(x, whi, wlo, 3, 1, y, cop, cip, **kw)
 torch.cuda.synchronize()
-d = dbg.cpu().view(3, 32, 4)
+ep = dbg.cpu()[384:]
+d = dbg.cpu()[:384].view(3, 32, 4)
 t0 = int(d[0, 0, 0])
 print("shape ci%d co%d r%d mode %s; all times in cycles relative to the producer's first stamp" % (ci, co, r, mode))
 print("tile | prod: start, halo_empty_ok | mma: start, acc_empty_ok, halo_full_ok, committed | epi: start, acc_full_ok, drained, flushed")
@@ -38,3 +39,9 @@ for t in range(12):
     print("%4d | %s %s | %s %s %s %s | %s %s %s %s" % ((t,) + tuple(f(v) for v in list(d[0, t, :2]) + list(d[1, t]) + list(d[2, t]))))
 per = (int(d[1, 11, 3]) - int(d[1, 3, 3])) / 8.0
 print("steady-state cycles per tile (MMA commit to commit): %.0f ; epilogue drain time per tile: %.0f" % (per, float((d[2, 3:11, 2] - d[2, 3:11, 1]).double().mean())))
+
+print("epilogue of tile 4, per plane: [start, side-loads issued, chunks staged, fence done, wait_read done, barrier done, store issued] deltas")
+for dpl in range(4):
+    v = [int(ep[dpl * 8 + i]) for i in range(7)]
+    if v[0]:
+        print("  plane %d:" % dpl, [v[i + 1] - v[i] for i in range(6)], " total", v[6] - v[0])

@@ -1,0 +1,20 @@
+"""tcgen05.mma throughput vs N / layout / descriptor shape (cycles per M=128,K=16 MMA, one issuing warp per SM)."""
+import importlib, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("3dunetcnn_b200")
+L = pkg.lib
+lib = L.load_library()
+SW = {"none": 0, "sw128": 2, "sw64": 4, "sw32": 6}
+out = torch.zeros(148, dtype=torch.int64, device="cuda")
+print("%-6s %-6s %6s %6s %6s | cycles/MMA  -> TFLOP/s (148 SMs @1.9GHz)" % ("N", "layout", "a_sbo", "b_sbo", "a_step"))
+for layout, rb in (("sw64", 64), ("sw32", 32), ("sw128", 128)):
+    for N in (16, 32, 64, 96, 128, 192, 256):
+        for (a_sbo, a_step) in ((8 * rb, 32), (10 * rb, 32), (10 * rb, rb * 180)):
+            inner, reps = 8, 400
+            L.check(lib.b200unet_umma_rate(N, SW[layout], a_sbo, 8 * rb, a_step % 32768, inner, reps, 148, out.data_ptr(), L.stream_ptr()))
+            torch.cuda.synchronize()
+            cyc = out.double().mean().item() / (inner * reps)
+            tf = 2 * 128 * N * 16 / cyc * 148 * 1.9e9 / 1e12
+            print("%-6d %-6s %6d %6d %6d | %7.1f   %7.0f" % (N, layout, a_sbo, 8 * rb, a_step, cyc, tf), flush=True)
