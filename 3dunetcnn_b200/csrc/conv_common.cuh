@@ -229,9 +229,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t t
           const float s1 = warp_colsum16(v, lane);
           const float s2 = warp_colsum16(q, lane);
           if ((lane & 1) == 0) {
-            const int col = j * 16 + ((lane >> 1) & 15);
-            atomicAdd(&s_stats[col * 2 + 0], s1);
-            atomicAdd(&s_stats[col * 2 + 1], s2);
+            // s_stats: one private [BN][2] slot per epilogue warp (no shared-memory float atomics: they are CAS loops)
+            float2* mine = reinterpret_cast<float2*>(s_stats) + (lane_base >> 5) * BN + j * 16 + ((lane >> 1) & 15);
+            float2 acc = *mine;
+            acc.x += s1; acc.y += s2;
+            *mine = acc;
           }
         }
       }

@@ -41,12 +41,13 @@ struct HaloCfg {
   static constexpr int NACC = (2 * TD * BN <= 512) ? 2 : 1;
   static constexpr int ACC_COLS = NACC * TD * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;   // barriers | stats | GN coefficients
+  static constexpr int AUX_BYTES = 1024 + 8 * BN * 2 * 4 + BN * 16;   // barriers | per-warp stats | GN coefficients
   static constexpr int BUDGET = 232448 - 1024;                   // dynamic smem limit minus alignment slack
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
   static constexpr uint32_t SBO_B = 8 * RB;
-  static constexpr bool RUN = BN <= 32;                     // register-resident running statistics
+  static constexpr bool COLSPLIT = BN >= 64;                // epilogue groups split the columns (else the planes)
+  static constexpr bool RUN = BN <= 64;                     // register-resident running statistics (<= 32 columns per thread)
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
   static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
 };
@@ -56,7 +57,7 @@ struct HaloArgs {
   int ntiles;        // output-channel tiles
   int hsplit;        // the halo box is loaded as (TD+2) * hsplit TMA boxes of (KC, 10, 18/hsplit, 1)
   int nb;            // weight ring depth (stages of TPB taps)
-  int nout;          // output staging buffers (1 or 2), each OUT_TILE * (split ? 2 : 1) bytes
+  int nout;          // output staging buffers (2 or 4), each OUT_TILE * (split ? 2 : 1) bytes
   int split;
   long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
   uint64_t* acc_empty = acc_full + Cfg::NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::NACC);
   float* s_stats = reinterpret_cast<float*>(aux + 1024);
-  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + BN * 8);
+  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + 8 * BN * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,19 +217,28 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // 8 warps in two groups of 4 (one warp per TMEM lane quadrant in each group): group g drains the planes
-    // dpl = g, g+2, ... of every tile into its own staging buffers, so two planes are in flight per SM and every
-    // scheduler interleaves two epilogue warps (a single warp per scheduler ran latency-bound at ~600 cycles per
-    // 16-column chunk: profiles/r01_halo_timeline.txt).
+    // 8 warps in two groups of 4 (one warp per TMEM lane quadrant in each group), so two drains are in flight per SM
+    // and every scheduler interleaves two epilogue warps (a single warp per scheduler ran latency-bound at ~600 cycles
+    // per 16-column chunk: profiles/r01_halo_timeline.txt).
+    //   BN <= 32 (plane split): group g drains the planes dpl = g, g+2, ... into its own staging buffers.
+    //   BN >= 64 (column split): both groups drain every plane, group g the column half [g*BN/2, (g+1)*BN/2), into a
+    //   shared staging buffer; a thread then owns <= 32 (BN=64) columns, so the running statistics fit in registers.
+    // Side inputs (residual / norm input) are software-pipelined: the rows of the NEXT 32-column group (of this plane or
+    // of the next one) are requested as soon as the registers of the current group have been consumed.
     constexpr bool RUN = Cfg::RUN;
-    constexpr int NCH = BN / 16;
-    constexpr int NACCUM = RUN ? BN : 16;
+    constexpr bool COLS = Cfg::COLSPLIT;
+    constexpr int NJ = COLS ? BN / 32 : BN / 16;      // 16-column chunks a thread drains per plane
+    constexpr int NACCUM = RUN ? NJ * 16 : 16;
+    constexpr int SG = NJ < 2 ? NJ : 2;               // chunks per side-input group
+    constexpr int NSG = NJ / SG;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const int e = threadIdx.x - 64;           // 0..255
-    const int grp = (warp - 2) >> 2;          // plane-parity group
-    const int issuer = 64 + grp * 128;        // the thread of this group that issues its TMA stores
-    const int nog = hp.nout >> 1;             // staging buffers per group (1 or 2)
+    const int grp = (warp - 2) >> 2;
+    const int jb = COLS ? grp * NJ : 0;       // first chunk of this thread
+    const int issuer = COLS ? 64 : 64 + grp * 128;   // the thread that issues the TMA stores (of its group)
+    const int nog = COLS ? hp.nout : hp.nout >> 1;   // staging buffers this thread's group rotates through
+    const int pstep = COLS ? 1 : 2;
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
     const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
     const bf16* side_lo = p.mode == 0 ? p.res_lo : p.x_lo;
@@ -239,25 +249,30 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
     float rs[NACCUM], rq[NACCUM];
 #pragma unroll
     for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
-    for (int i = e; i < BN * 2; i += 256) s_stats[i] = 0.f;
+    for (int i = e; i < 8 * BN * 2; i += 256) s_stats[i] = 0.f;
     asm volatile("bar.sync 3, 256;" ::: "memory");
     uint32_t ti = 0, oi = 0;   // tile counter, output-plane counter (staging ring)
     int cur_n = -1, cur_n0 = -1;
+    auto group_sync = [&]() {
+      if (COLS) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
 
-    // s_stats (holding every warp's partial sums) -> global fp64 atomics, then re-zero
+    // s_stats holds one private [BN][2] slot per epilogue warp (shared-memory float atomics are CAS spin loops and
+    // collapse under 8-warp contention); the flush sums the slots -> global fp64 atomics, then re-zeroes them
+    float2* s_mine = reinterpret_cast<float2*>(s_stats) + (warp - 2) * BN;
     auto flush_smem = [&](int fn, int fn0) {
       asm volatile("bar.sync 3, 256;" ::: "memory");
-      for (int c = e; c < BN; c += 256) {
-        if (fn0 + c < p.Cout) {
-          atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
-          atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
-        }
-        s_stats[c * 2 + 0] = 0.f;
-        s_stats[c * 2 + 1] = 0.f;
+      for (int c = e; c < BN * 2; c += 256) {
+        float v = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) { v += s_stats[wq * BN * 2 + c]; s_stats[wq * BN * 2 + c] = 0.f; }
+        if (fn0 + (c >> 1) < p.Cout) atomicAdd(&stat_dst[((long long)fn * stat_ld + fn0) * 2 + c], (double)v);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     };
-    // register accumulators of chunk j -> transposing butterfly -> s_stats
+    // register accumulators of chunk j -> transposing butterfly -> this warp's s_stats slot
     auto reduce_chunk = [&](int j, const float* sv, const float* sq) {
       float v16[16], q16[16];
 #pragma unroll
@@ -265,8 +280,22 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
       const float s1 = warp_colsum16(v16, lane), s2 = warp_colsum16(q16, lane);
       if ((lane & 1) == 0) {
         const int col = j * 16 + ((lane >> 1) & 15);
-        atomicAdd(&s_stats[col * 2 + 0], s1);
-        atomicAdd(&s_stats[col * 2 + 1], s2);
+        float2 acc = s_mine[col];
+        acc.x += s1; acc.y += s2;
+        s_mine[col] = acc;
+      }
+    };
+    // side-input rows of chunk group sg (SG chunks of 16 channels) of the voxel row at vx
+    uint4 sh[2 * SG], sl[2 * SG];
+    auto load_side = [&](long long vx, int n0, int sg, bool ok) {
+      if (!side_hi || !ok) return;
+#pragma unroll
+      for (int c = 0; c < 2 * SG; ++c) {
+        const int cc = n0 + (jb + sg * SG) * 16 + c * 8;
+        if (cc < p.Cout) {
+          sh[c] = *reinterpret_cast<const uint4*>(side_hi + vx * side_ld + cc);
+          if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vx * side_ld + cc);
+        }
       }
     };
 
@@ -281,7 +310,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
       if (n != cur_n || n0 != cur_n0) {
         if (RUN && want_stats && cur_n >= 0) {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) reduce_chunk(j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
+          for (int j = 0; j < NJ; ++j) reduce_chunk(jb + j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
 #pragma unroll
           for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
           flush_smem(cur_n, cur_n0);
@@ -298,42 +327,33 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
       const bool valid_wh = (w < p.Wo) && (h < p.Ho);
       const long long vox0 = (((long long)n * p.Do + d0) * p.Ho + h) * p.Wo + w;   // plane dpl: + dpl * Ho * Wo
       const long long plane = (long long)p.Ho * p.Wo;
-      for (int dpl = grp; dpl < TD; dpl += 2)     // side-input rows of this group's planes -> L2 while the MMAs still run
-        conv_epilogue_prefetch(p, n0, BN, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
+      const int dpl0 = COLS ? 0 : grp;
+      load_side(vox0 + dpl0 * plane, n0, 0, valid_wh && (d0 + dpl0 < p.Do) && dpl0 < TD);   // lands while the MMAs still run
+      for (int dpl = dpl0 + pstep; dpl < TD; dpl += pstep)     // the later planes' rows -> L2
+        conv_epilogue_prefetch(p, n0 + jb * 16, NJ * 16, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
       const uint32_t as = ti % Cfg::NACC;
       if (warp == 2) HALO_STAMP(2, 0);
       mbar_wait(&acc_full[as], (ti / Cfg::NACC) & 1);
       tc_fence_after();
       if (warp == 2) HALO_STAMP(2, 1);
 #pragma unroll 1
-      for (int dpl = grp; dpl < TD; dpl += 2, ++oi) {
+      for (int dpl = dpl0; dpl < TD; dpl += pstep, ++oi) {
         const int d = d0 + dpl;
         const bool valid = valid_wh && (d < p.Do);
         const long long vox = vox0 + dpl * plane;
-        uint8_t* stage = smem_out + (grp * nog + (oi % nog)) * out_buf_bytes;
+        const bool valid_next = valid_wh && (dpl + pstep < TD) && (d + pstep < p.Do);
+        uint8_t* stage = smem_out + ((COLS ? 0 : grp * nog) + (oi % nog)) * out_buf_bytes;
         EPI_STAMP(dpl * 8 + 0);
-        // side input (residual / norm input): preloaded for groups of two 16-column chunks (one latency per 32 columns)
-        constexpr int SG = NCH < 2 ? NCH : 2;
-        uint4 sh[2 * SG], sl[2 * SG];
-        if (nog == 1) {   // single staging buffer per group: its previous store must have finished reading it
+        if (nog == 1) {   // single staging buffer: its previous store must have finished reading it
           if (threadIdx.x == issuer) tma_store_wait_read0();
-          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          group_sync();
         }
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = jb + jj;
           const int c0 = n0 + j * 16;
-          float* as_ = rs + (RUN ? j * 16 : 0);
-          float* aq_ = rq + (RUN ? j * 16 : 0);
-          if ((j % SG) == 0 && side_hi && valid) {
-#pragma unroll
-            for (int c = 0; c < 2 * SG; ++c) {
-              if (c0 + c * 8 < p.Cout) {
-                sh[c] = *reinterpret_cast<const uint4*>(side_hi + vox * side_ld + c0 + c * 8);
-                if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vox * side_ld + c0 + c * 8);
-              }
-            }
-          }
+          float* as_ = rs + (RUN ? jj * 16 : 0);
+          float* aq_ = rq + (RUN ? jj * 16 : 0);
           if (c0 < p.Cout) {
             uint32_t r[16];
             tmem_ld16(tmem_base + (as * TD + dpl) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
@@ -349,11 +369,11 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[hf * 8 + i]);
                 if (side_hi) {
-                  const uint4 a = sh[(j % SG) * 2 + hf];
+                  const uint4 a = sh[(jj % SG) * 2 + hf];
                   sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
                   sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
                   if (side_lo) {
-                    const uint4 b = sl[(j % SG) * 2 + hf];
+                    const uint4 b = sl[(jj % SG) * 2 + hf];
                     sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
                     sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);
                   }
@@ -411,6 +431,11 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
               for (int i = 0; i < 16; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
             }
           }
+          // the registers of this side-input group are consumed: request the next group (this plane's, else the next plane's)
+          if ((jj % SG) == SG - 1) {
+            if (jj / SG + 1 < NSG) load_side(vox, n0, jj / SG + 1, valid);
+            else load_side(vox + pstep * plane, n0, 0, valid_next);
+          }
         }
         // the plane is staged: make it visible to the async proxy, then one thread TMA-stores it
         EPI_STAMP(dpl * 8 + 2);
@@ -418,8 +443,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
         EPI_STAMP(dpl * 8 + 3);
         if (nog > 1 && threadIdx.x == issuer) tma_store_wait_read0();   // the other buffer is free again after the barrier
         EPI_STAMP(dpl * 8 + 4);
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        group_sync();
         EPI_STAMP(dpl * 8 + 5);
         if (threadIdx.x == issuer && d < p.Do) {
 #pragma unroll
@@ -442,7 +466,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
     }
     if (RUN && want_stats && cur_n >= 0) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) reduce_chunk(j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
+      for (int j = 0; j < NJ; ++j) reduce_chunk(jb + j, rs + (RUN ? j * 16 : 0), rq + (RUN ? j * 16 : 0));
       flush_smem(cur_n, cur_n0);
     }
     if (threadIdx.x == issuer) tma_store_wait_all();   // all output tiles have left shared memory and are written
@@ -457,7 +481,8 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   // shared-memory carve-up: 2 halo buffers | nout output staging buffers | weight ring | aux
   const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
-  h.nout = (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;   // staging buffers: 2 per plane-parity group if they fit
+  // staging buffers: column-split groups share a ring of 2; plane-split groups own 2 each if they fit, else 1 each
+  h.nout = Cfg::COLSPLIT ? 2 : (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
   B200_REQUIRE(nb >= 2, E_UNSUPPORTED, "conv_halo: configuration KC=%d BN=%d TD=%d does not fit shared memory", KC, BN, TD);
@@ -490,7 +515,7 @@ static bool halo_fits(int KC, int BN, int TD, bool split) {
   const int halo = (180 * (TD + 2) * KC * 2 + 1023) / 1024 * 1024;
   const int tpb = BN <= 64 ? 3 : 1;
   const int bbytes = (tpb * BN * KC * 2 + 1023) / 1024 * 1024;
-  const int aux = 1024 + BN * 8 + BN * 16;
+  const int aux = 1024 + 8 * BN * 8 + BN * 16;
   const int out_buf = 128 * BN * 2 * (split ? 2 : 1);
   return 232448 - 1024 - aux - 2 * halo - 2 * out_buf >= 2 * bbytes;
 }

@@ -32,7 +32,7 @@ struct ConvCfg {
   static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int AUX_BYTES = 1024 + BN * 2 * 4 + BN * 16;  // barriers+slot | stats | coef
+  static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4 + BN * 16;  // barriers+slot | per-warp stats | coef
   static constexpr int OUT_STAGING = 2 * 128 * BN * 2;    // hi + lo output tiles, aliased onto the pipeline stages
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES > OUT_STAGING ? STAGES * STAGE_BYTES : OUT_STAGING;
   static constexpr int SMEM_BYTES = PIPE_BYTES + AUX_BYTES + 1024;  // +1024 alignment slack
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-  float* s_stats = reinterpret_cast<float*>(aux + 1024);             // [BN][2]
-  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + BN * 8);   // [BN]
+  float* s_stats = reinterpret_cast<float*>(aux + 1024);             // [4 warps][BN][2]
+  float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + 4 * BN * 8);   // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   }
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
-    for (int i = e; i < BN * 2; i += 128) s_stats[i] = 0.f;
+    for (int i = e; i < 4 * BN * 2; i += 128) s_stats[i] = 0.f;
     if (p.mode == 1) {
       for (int c = e; c < BN; c += 128)
         s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -179,11 +179,9 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
       const int e = threadIdx.x - 64;
       double* dst = (p.mode == 0) ? p.stats : p.bstats;
       const int ld = (p.mode == 0) ? p.stats_ld : p.coef_ld;
-      for (int c = e; c < BN; c += 128) {
-        if (n0 + c < p.Cout) {
-          atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 0], (double)s_stats[c * 2 + 0]);
-          atomicAdd(&dst[((long long)n * ld + n0 + c) * 2 + 1], (double)s_stats[c * 2 + 1]);
-        }
+      for (int c = e; c < BN * 2; c += 128) {
+        const float v = s_stats[c] + s_stats[BN * 2 + c] + s_stats[2 * BN * 2 + c] + s_stats[3 * BN * 2 + c];
+        if (n0 + (c >> 1) < p.Cout) atomicAdd(&dst[((long long)n * ld + n0) * 2 + c], (double)v);
       }
     }
     if (threadIdx.x == 64) tma_store_wait_all();   // the staging tile must outlive the bulk store

@@ -75,16 +75,20 @@ __global__ void __launch_bounds__(128) k_umma_probe(int layout_mode, int start_o
 // on resident (zeroed) shared-memory operands and reports clock64 cycles per MMA.  a_sbo / layout / a_step let the
 // caller mimic the halo kernel's shifted, re-strided A descriptors.
 __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps,
-                                                  long long* __restrict__ out) {
+                                                  long long* __restrict__ out, const uint8_t* __restrict__ copy_src,
+                                                  int copy_bytes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 160 * 1024);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* cbar = bar + 1;                                     // copy-warp barrier
+  volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(bar + 2);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 3);
+  if (threadIdx.x == 0) *done = 0;
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
-    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(cbar, 1); fence_barrier_init(); }
     __syncwarp();
     tmem_alloc(slot, 512);
     tmem_relinquish();
@@ -109,17 +113,37 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
     umma_commit_if(issue, bar);
     mbar_wait(bar, 0);
     const long long t1 = clock64();
-    if (lane == 0) out[blockIdx.x] = t1 - t0;
+    if (lane == 0) { out[blockIdx.x] = t1 - t0; *done = 1; }
+  } else if (copy_bytes > 0 && lane == 0) {
+    // operand-write pressure: bulk copies global (L2-resident) -> shared memory region [128K, 160K) until the MMAs finish
+    long long copied = 0;
+    uint32_t ph = 0;
+    const uint32_t dst = smem_u32(smem + 128 * 1024), mb = smem_u32(cbar);
+    const uint8_t* src = copy_src + (size_t)blockIdx.x * 32768;
+    while (*done == 0) {
+      const uint32_t q = copy_bytes / 4;   // four copies in flight per round
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(4 * q) : "memory");
+#pragma unroll
+      for (uint32_t c = 0; c < 4; ++c)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + c * q),
+                     "l"(src + c * q), "r"(q), "r"(mb)
+                     : "memory");
+      mbar_wait(cbar, ph);
+      ph ^= 1;
+      copied += 4 * q;
+    }
+    out[gridDim.x + blockIdx.x] = copied;
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 int launch_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, long long* out,
-                     cudaStream_t st) {
+                     const void* copy_src, int copy_bytes, cudaStream_t st) {
+  B200_REQUIRE(copy_bytes >= 0 && copy_bytes <= 32768 && copy_bytes % 64 == 0, E_INVALID, "umma_rate: copy_bytes=%d", copy_bytes);
   const int smem = 160 * 1024 + 64 + 1024;
   B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out);
+  k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out, reinterpret_cast<const uint8_t*>(copy_src), copy_bytes);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -166,9 +166,11 @@ int b200unet_plan_profile_dump(b200unet_plan* plan, const char* path);
 
 /* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
 int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
-/* tcgen05.mma issue-rate micro-benchmark (M=128, N=n, K=16): cycles for reps*inner MMAs per CTA -> out[cta] */
+/* tcgen05.mma issue-rate micro-benchmark (M=128, N=n, K=16): cycles for reps*inner MMAs per CTA -> out[cta].
+ * copy_bytes > 0: a second warp streams bulk copies of copy_bytes (<= 32768, multiple of 16) from copy_src into
+ * shared memory for the whole duration (operand-write pressure); bytes copied per CTA -> out[ctas + cta]. */
 int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
-                       void* stream);
+                       const void* copy_src, int copy_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,3 +17,5 @@ for a in "32 32 128 plain" "32 64 128 mode1" "32 32 128 res"; do timeout 120 pyt
 ( timeout 600 python tools/conv_bench.py all 10 2>&1 | grep convbench ) | tee gpurun_out/convbench13.log | cut -c1-330
 timeout 300 python tools/layer_times.py gpurun_out/layer_times13.csv 2>&1 | tail -3 | cut -c1-400
 ( timeout 400 python tools/gpu_diag.py model 2>&1 | grep diag ) | cut -c1-200
+echo "--- MAXC=256"
+( B200UNET_HALO_MAXC=256 timeout 600 python tools/conv_bench.py all 10 2>&1 | grep convbench ) | grep -E '"ci": (128|256)|total' | cut -c1-330

@@ -40,8 +40,8 @@ for t in range(12):
 per = (int(d[1, 11, 3]) - int(d[1, 3, 3])) / 8.0
 print("steady-state cycles per tile (MMA commit to commit): %.0f ; epilogue drain time per tile: %.0f" % (per, float((d[2, 3:11, 2] - d[2, 3:11, 1]).double().mean())))
 
-print("epilogue of tile 4, per plane: [start, side-loads issued, chunks staged, fence done, wait_read done, barrier done, store issued] deltas")
+print("epilogue of tile 4, per plane: deltas [chunks staged, fence done, wait_read done, barrier done, store issued]")
 for dpl in range(4):
-    v = [int(ep[dpl * 8 + i]) for i in range(7)]
+    v = [int(ep[dpl * 8 + i]) for i in (0, 2, 3, 4, 5, 6)]
     if v[0]:
-        print("  plane %d:" % dpl, [v[i + 1] - v[i] for i in range(6)], " total", v[6] - v[0])
+        print("  plane %d:" % dpl, [v[i + 1] - v[i] for i in range(5)], " total", v[5] - v[0])
