@@ -162,10 +162,10 @@ int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stre
 }
 
 int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
-                       const void* copy_src, int copy_bytes, void* stream) {
+                       const void* copy_src, int copy_bytes, int commit_each_rep, void* stream) {
   NOT_NULL(out);
   return launch_umma_rate(n, layout, a_sbo, b_sbo, a_step, inner, reps, ctas, reinterpret_cast<long long*>(out), copy_src,
-                          copy_bytes, to_stream(stream));
+                          copy_bytes, commit_each_rep, to_stream(stream));
 }
 
 }  // extern "C"

@@ -46,6 +46,7 @@ struct HaloCfg {
   static constexpr uint32_t LAYOUT = KC == 64 ? UMMA_SW128 : KC == 32 ? UMMA_SW64 : UMMA_SW32;
   static constexpr uint32_t SBO_A = 10 * RB;                // one halo row (10 voxels) per 8-row group
   static constexpr uint32_t SBO_B = 8 * RB;
+  static constexpr bool STK = BN <= 64;                     // kd taps stacked along N (one MMA feeds <= 3 output planes)
   static constexpr bool COLSPLIT = BN >= 64;                // epilogue groups split the columns (else the planes)
   static constexpr bool RUN = BN <= 64;                     // register-resident running statistics (<= 32 columns per thread)
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
@@ -67,7 +68,7 @@ struct HaloArgs {
   do { if (hp.dbg && blockIdx.x == 0 && ti < 32 && lane == 0) hp.dbg[((role) * 32 + ti) * 4 + (slot)] = clock64(); } while (0)
 
 template <int KC, int BN, int TD>
-__global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
+__global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
                                                       const HaloArgs hp) {
   using Cfg = HaloCfg<KC, BN, TD>;
   extern __shared__ uint8_t smem_raw[];
@@ -117,8 +118,12 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
   const int groups0 = p.kchunks[0], groups1 = p.ntaps[1] ? p.kchunks[1] : 0;
   constexpr int STAGES0 = 27 / Cfg::TPB;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
+  if (warp == 0 || warp == 10) {
+    // ------------------------------------------------------------------ TMA producers (convergent, one lane issues)
+    // warp 10 loads the halo boxes, warp 0 the weight stages: with a single producer the next halo could only be
+    // requested after the last weight stage of the current chunk had been issued (<= nb stages before it is needed),
+    // which left the MMA warp waiting ~1K cycles at every chunk / tile boundary (HALO_STAMP timeline).
+    const bool halo_role = warp == 10;
     const uint32_t issue = elect_one() ? 1u : 0u;
     uint32_t hi = 0, bi = 0, ti = 0;
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
@@ -129,13 +134,13 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
       const int dt = t % p.tiles_d;
       const int n = t / p.tiles_d;
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
-      HALO_STAMP(0, 0);
+      if (halo_role) HALO_STAMP(0, 0);
       for (int g = 0; g < groups0 + groups1; ++g) {
         const int src = g < groups0 ? 0 : 1;
         const int kc = src == 0 ? g : g - groups0;
         const int nstage = src == 0 ? STAGES0 : 1;
         for (int pass = 0; pass < p.npass; ++pass) {
-          {
+          if (halo_role) {
             const uint32_t s = hi % Cfg::NHALO, ph = (hi / Cfg::NHALO) & 1;
             mbar_wait(&halo_empty[s], ph ^ 1);
             HALO_STAMP(0, 1);
@@ -146,14 +151,18 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
                 tma_load_5d_if(issue, smem_halo + s * Cfg::HALO_BYTES + ((dp * 18 + hq * hrows) * 10) * Cfg::RB,
                                &maps.a[src][pass == 1], &halo_full[s], kc * KC, w0 - 1, h0 - 1 + hq * hrows, d0 - 1 + dp, n);
             ++hi;
-          }
-          for (int st = 0; st < nstage; ++st) {
-            const uint32_t s = bi % NB, ph = (bi / NB) & 1;
-            mbar_wait(&b_empty[s], ph ^ 1);
-            mbar_expect_tx_if(issue, &b_full[s], src == 0 ? Cfg::B_TX : Cfg::B_TAP);
-            tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0,
-                           src == 0 ? st * Cfg::TPB : 0);
-            ++bi;
+          } else {
+            for (int st = 0; st < nstage; ++st) {
+              const uint32_t s = bi % NB, ph = (bi / NB) & 1;
+              mbar_wait(&b_empty[s], ph ^ 1);
+              mbar_expect_tx_if(issue, &b_full[s], src == 0 ? Cfg::B_TX : Cfg::B_TAP);
+              if (Cfg::STK && src == 0)   // stage st = (kh,kw): the three kd taps through the 4-D (Cin, Cout, khkw, kd) view
+                tma_load_4d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, st, 0);
+              else
+                tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0,
+                               src == 0 ? st * Cfg::TPB : 0);
+              ++bi;
+            }
           }
         }
       }
@@ -161,6 +170,8 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (convergent, one lane issues)
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, BN * 2 <= 256 ? BN * 2 : BN, 0, 0);
+    constexpr uint32_t idesc3 = make_idesc_bf16(128, BN * 3 <= 256 ? BN * 3 : BN, 0, 0);
     constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT);
     constexpr uint32_t hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT);
     const uint32_t issue = elect_one() ? 1u : 0u;
@@ -188,6 +199,39 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
             mbar_wait(&b_full[bs], (bi / NB) & 1);
             tc_fence_after();
             const uint32_t b_lo0 = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
+            if (Cfg::STK && src == 0) {
+              // kd-stacked issue: stage st = (kh,kw) holds the weight tiles of kd = 0,1,2 back to back (3*BN rows).
+              // Halo plane hq feeds output planes hq-kd; accumulators sit in DESCENDING plane order in TMEM, so one MMA
+              // with N = nkd*BN columns starting at plane (hq-kdmin) covers them: N = 32 costs 46 cycles, N = 96 only 56
+              // (tools/umma_rate.py), i.e. 6 MMAs (304 cycles) replace 12 (552) per (kh,kw,k16) at TD = 4.
+              const int kh = st / 3, kw = st - kh * 3;
+              const uint32_t a_base = halo_lo + (((kh * 10 + kw) * Cfg::RB) >> 4);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                if (first && k == 0) {
+                  // very first K step of the tile: unstacked, the kd = 0 MMA of every plane overwrites its accumulator
+#pragma unroll
+                  for (int dpl = 0; dpl < TD; ++dpl) {
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd)
+                      umma_bf16_if(issue, acc0 + (TD - 1 - dpl) * BN, desc_from(a_base + (((dpl + kd) * 180 * Cfg::RB) >> 4), hi_a),
+                                   desc_from(b_lo0 + ((kd * Cfg::B_TAP) >> 4), hi_b), idesc, kd > 0 ? 1u : 0u);
+                  }
+                  first = 0;
+                } else {
+#pragma unroll
+                  for (int hq = 0; hq < TD + 2; ++hq) {
+                    const int kdmin = hq - (TD - 1) > 0 ? hq - (TD - 1) : 0;
+                    const int kdmax = hq < 2 ? hq : 2;
+                    const int nkd = kdmax - kdmin + 1;
+                    const uint32_t idn = nkd == 1 ? idesc : nkd == 2 ? idesc2 : idesc3;
+                    umma_bf16_if(issue, acc0 + (TD - 1 - hq + kdmin) * BN,
+                                 desc_from(a_base + ((hq * 180 * Cfg::RB + k * 32) >> 4), hi_a),
+                                 desc_from(b_lo0 + ((kdmin * Cfg::B_TAP + k * 32) >> 4), hi_b), idn, 1u);
+                  }
+                }
+              }
+            } else {
 #pragma unroll
             for (int tp = 0; tp < Cfg::TPB; ++tp) {
               if (src == 1 && tp > 0) break;
@@ -199,11 +243,13 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
               for (int dpl = 0; dpl < TD; ++dpl) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16_if(issue, acc0 + dpl * BN, desc_from(a_lo + ((dpl * 180 * Cfg::RB + k * 32) >> 4), hi_a),
+                  umma_bf16_if(issue, acc0 + (Cfg::STK ? TD - 1 - dpl : dpl) * BN,
+                               desc_from(a_lo + ((dpl * 180 * Cfg::RB + k * 32) >> 4), hi_a),
                                desc_from(b_lo + (k * 32 >> 4), hi_b), idesc, (k == 0) ? (first ^ 1u) : 1u);
                 }
               }
               first = 0;
+            }
             }
             umma_commit_if(issue, &b_empty[bs]);
             ++bi;
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_halo(const __grid_constant__ Co
           float* aq_ = rq + (RUN ? jj * 16 : 0);
           if (c0 < p.Cout) {
             uint32_t r[16];
-            tmem_ld16(tmem_base + (as * TD + dpl) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
+            tmem_ld16(tmem_base + (as * TD + (Cfg::STK ? TD - 1 - dpl : dpl)) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
             tmem_ld_wait();
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -483,6 +529,11 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
   // staging buffers: column-split groups share a ring of 2; plane-split groups own 2 each if they fit, else 1 each
   h.nout = Cfg::COLSPLIT ? 2 : (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;
+  if (const char* e = getenv("B200UNET_HALO_NOUT")) {   // tuning override
+    const int v = atoi(e);
+    if ((v == 2 || v == 4) && (Cfg::COLSPLIT || v == 4 || true)) h.nout = Cfg::COLSPLIT ? 2 : v;
+    if (v == 1 && Cfg::COLSPLIT) h.nout = 1;
+  }
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
   B200_REQUIRE(nb >= 2, E_UNSUPPORTED, "conv_halo: configuration KC=%d BN=%d TD=%d does not fit shared memory", KC, BN, TD);
@@ -495,7 +546,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
     B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD><<<grid, 320, smem_bytes, st>>>(maps, a, h);
+  k_conv_halo<KC, BN, TD><<<grid, 352, smem_bytes, st>>>(maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -577,11 +628,14 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     const int boxT = (s == 0) ? tpb : 1;
     B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz,
                           c.x.vD, c.x.vH, c.x.vW));
-    B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
+    const bool stk = (s == 0) && BN <= 64;   // kd-stacked weight stages: 4-D view (Cin, Cout, khkw, kd), box (KC, BN, 1, 3)
+    if (stk) B200_TRY(make_w_map_kd(&maps.b[s][0], c.w_hi, op.Cop, c.Cip, KC, BN, swz));
+    else B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
     if (split) {
       B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, 10, 18 / hsplit, 1, 1, swz,
                             c.x.vD, c.x.vH, c.x.vW));
-      B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
+      if (stk) B200_TRY(make_w_map_kd(&maps.b[s][1], c.w_lo, op.Cop, c.Cip, KC, BN, swz));
+      else B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
     }
   }
   // output tile stores: box (min(BN,64) channels, 8, 16, 1, 1), swizzle by the box row bytes

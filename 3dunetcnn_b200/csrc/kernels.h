@@ -105,6 +105,6 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st);
 // out: device float [ntests][2][128][64]  (encoding 0: A[r][k]=r, encoding 1: A[r][k]=k; B = identity) -> D[m][n]
 int launch_umma_probe(const int* tests, int ntests, float* out, cudaStream_t st);
 int launch_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, long long* out,
-                     const void* copy_src, int copy_bytes, cudaStream_t st);
+                     const void* copy_src, int copy_bytes, int commit_each_rep, cudaStream_t st);
 
 }  // namespace b200

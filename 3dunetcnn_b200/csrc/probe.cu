@@ -76,19 +76,20 @@ __global__ void __launch_bounds__(128) k_umma_probe(int layout_mode, int start_o
 // caller mimic the halo kernel's shifted, re-strided A descriptors.
 __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps,
                                                   long long* __restrict__ out, const uint8_t* __restrict__ copy_src,
-                                                  int copy_bytes) {
+                                                  int copy_bytes, int commit_each_rep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 160 * 1024);
   uint64_t* cbar = bar + 1;                                     // copy-warp barrier
   volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(bar + 2);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 3);
+  uint64_t* sbar = bar + 3;                                     // per-"stage" commit target (never waited on)
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
   if (threadIdx.x == 0) *done = 0;
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
-    if (lane == 0) { mbar_init(bar, 1); mbar_init(cbar, 1); fence_barrier_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(cbar, 1); mbar_init(sbar, 1); fence_barrier_init(); }
     __syncwarp();
     tmem_alloc(slot, 512);
     tmem_relinquish();
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
       for (int i = 0; i < inner; ++i)
         umma_bf16_if(issue, tm + (i & 1) * 256, desc_from(a_lo + ((i * a_step) >> 4), hi_a), desc_from(b_lo + ((i & 3) * 2), hi_b),
                      idesc, 1u);
+      if (commit_each_rep) umma_commit_if(issue, sbar);
     }
     umma_commit_if(issue, bar);
     mbar_wait(bar, 0);
@@ -139,11 +141,11 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
 }
 
 int launch_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, long long* out,
-                     const void* copy_src, int copy_bytes, cudaStream_t st) {
+                     const void* copy_src, int copy_bytes, int commit_each_rep, cudaStream_t st) {
   B200_REQUIRE(copy_bytes >= 0 && copy_bytes <= 32768 && copy_bytes % 64 == 0, E_INVALID, "umma_rate: copy_bytes=%d", copy_bytes);
   const int smem = 160 * 1024 + 64 + 1024;
   B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out, reinterpret_cast<const uint8_t*>(copy_src), copy_bytes);
+  k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out, reinterpret_cast<const uint8_t*>(copy_src), copy_bytes, commit_each_rep);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

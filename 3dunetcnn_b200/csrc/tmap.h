@@ -16,6 +16,7 @@ int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, 
 
 // 3-D map over packed weights [T][R][K] bf16 (K contiguous): dims (K, R, T); box (boxK, boxR, 1).
 int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz, int boxT = 1);
+int make_w_map_kd(CUtensorMap* out, const bf16* ptr, int R, int K, int boxK, int boxR, Swz swz);
 
 static inline Swz swz_for_bytes(int bytes) { return bytes >= 128 ? SWZ_128 : bytes >= 64 ? SWZ_64 : SWZ_32; }
 

@@ -108,7 +108,7 @@ _SIGS = {
     "b200unet_plan_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "b200unet_plan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "b200unet_plan_profile_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
-    "b200unet_umma_rate": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200unet_umma_rate": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200unet_umma_probe": (C.c_int, [C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p]),
 }
 

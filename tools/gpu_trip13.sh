@@ -19,3 +19,4 @@ timeout 300 python tools/layer_times.py gpurun_out/layer_times13.csv 2>&1 | tail
 ( timeout 400 python tools/gpu_diag.py model 2>&1 | grep diag ) | cut -c1-200
 echo "--- MAXC=256"
 ( B200UNET_HALO_MAXC=256 timeout 600 python tools/conv_bench.py all 10 2>&1 | grep convbench ) | grep -E '"ci": (128|256)|total' | cut -c1-330
+B200UNET_HALO_MAXC=256 timeout 120 python tools/halo_timeline.py 128 128 64 plain 2>&1 | grep -v Warn | tail -8
