@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
   uint64_t* cbar = bar + 1;                                     // copy-warp barrier
   volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(bar + 2);
   uint64_t* sbar = bar + 3;                                     // per-"stage" commit target (never waited on)
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+  uint64_t* dbar = bar + 4;                                     // a barrier whose phase 0 is complete from the start
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 5);
   if (threadIdx.x == 0) *done = 0;
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
-    if (lane == 0) { mbar_init(bar, 1); mbar_init(cbar, 1); mbar_init(sbar, 1); fence_barrier_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(cbar, 1); mbar_init(sbar, 1); mbar_init(dbar, 1); mbar_arrive(dbar); fence_barrier_init(); }
     __syncwarp();
     tmem_alloc(slot, 512);
     tmem_relinquish();
@@ -110,7 +111,11 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
       for (int i = 0; i < inner; ++i)
         umma_bf16_if(issue, tm + (i & 1) * 256, desc_from(a_lo + ((i * a_step) >> 4), hi_a), desc_from(b_lo + ((i & 3) * 2), hi_b),
                      idesc, 1u);
-      if (commit_each_rep) umma_commit_if(issue, sbar);
+      // stage hand-back as a pipeline would do it: bit 0 commit, bit 1 wait on an (already complete) full barrier,
+      // bit 2 tcgen05.fence::after_thread_sync
+      if (commit_each_rep & 1) umma_commit_if(issue, sbar);
+      if (commit_each_rep & 2) mbar_wait(dbar, 0);
+      if (commit_each_rep & 4) tc_fence_after();
     }
     umma_commit_if(issue, bar);
     mbar_wait(bar, 0);
@@ -140,10 +145,77 @@ __global__ void __launch_bounds__(64) k_umma_rate(int N, int layout, int a_sbo, 
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- stage-structured issue benchmark: the MMA-warp loop of the conv kernels in isolation.  `nw` issuing warps take
+// the stages round-robin; a stage = wait on an (already complete) full barrier + tcgen05 fence + one elected lane issuing
+// `MPS` MMAs (M=128, N, K=16) and a commit.  Reports cycles for all stages (warp 0's clock).
+template <int MPS>
+__global__ void __launch_bounds__(64) k_umma_issue(int N, int stages, int nw, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 160 * 1024);
+  uint64_t* sbar = bar + 1;
+  uint64_t* dbar = bar + 2;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 3);
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) { mbar_init(bar, nw); mbar_init(sbar, 1); mbar_init(dbar, 1); mbar_arrive(dbar); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = __shfl_sync(0xffffffffu, *slot, 0);
+  if (warp < nw) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    constexpr uint32_t hi = desc_hi(1024, UMMA_SW128);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
+    uint32_t bs = warp, NB = 7;
+    const long long t0 = clock64();
+    for (int s = warp; s < stages; s += nw) {
+      mbar_wait(dbar, 0);
+      tc_fence_after();
+      const uint32_t alo = desc_lo(a0 + (s & 7) * 1024, 16), blo = desc_lo(b0 + bs * 4096, 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < MPS; ++i)
+          umma_bf16(tm + (i & 1) * 256, desc_from(alo + (i >> 1) * 2 + (i & 1) * 360, hi), desc_from(blo + (i >> 1) * 2, hi), idesc, 1u);
+        umma_commit(sbar);
+      }
+      __syncwarp();
+      bs += nw;
+      if (bs >= NB) bs -= NB;
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (warp == 0 && lane == 0) out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 int launch_umma_rate(int N, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, long long* out,
                      const void* copy_src, int copy_bytes, int commit_each_rep, cudaStream_t st) {
   B200_REQUIRE(copy_bytes >= 0 && copy_bytes <= 32768 && copy_bytes % 64 == 0, E_INVALID, "umma_rate: copy_bytes=%d", copy_bytes);
   const int smem = 160 * 1024 + 64 + 1024;
+  if (commit_each_rep & 24) {   // stage-structured issue benchmark: bit 3 = one issuing warp, bit 4 = two; inner = MMAs per stage
+    const int nw = (commit_each_rep & 16) ? 2 : 1;
+    B200_REQUIRE(inner == 4 || inner == 12, E_INVALID, "umma_rate: stage benchmark supports 4 or 12 MMAs per stage");
+    if (inner == 4) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_issue<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_umma_issue<4><<<ctas, 64, smem, st>>>(N, reps, nw, out);
+    } else {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_issue<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_umma_issue<12><<<ctas, 64, smem, st>>>(N, reps, nw, out);
+    }
+    B200_CHECK_CUDA(cudaGetLastError());
+    return OK;
+  }
   B200_CHECK_CUDA(cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   k_umma_rate<<<ctas, 64, smem, st>>>(N, layout, a_sbo, b_sbo, a_step, inner, reps, out, reinterpret_cast<const uint8_t*>(copy_src), copy_bytes, commit_each_rep);
   B200_CHECK_CUDA(cudaGetLastError());

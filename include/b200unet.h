@@ -169,7 +169,8 @@ int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stre
 /* tcgen05.mma issue-rate micro-benchmark (M=128, N=n, K=16): cycles for reps*inner MMAs per CTA -> out[cta].
  * copy_bytes > 0: a second warp streams bulk copies of copy_bytes (<= 32768, multiple of 16) from copy_src into
  * shared memory for the whole duration (operand-write pressure); bytes copied per CTA -> out[ctas + cta].
- * commit_each_rep != 0: a tcgen05.commit (to an unobserved mbarrier) follows every `inner` MMAs, as a pipeline stage would. */
+ * commit_each_rep: stage hand-back after every `inner` MMAs: bit 0 tcgen05.commit (to an unobserved mbarrier), bit 1 an
+ * mbarrier wait that succeeds immediately, bit 2 tcgen05.fence::after_thread_sync. */
 int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
                        const void* copy_src, int copy_bytes, int commit_each_rep, void* stream);
 

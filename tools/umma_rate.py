@@ -22,13 +22,26 @@ for N in (64, 128, 256):
         tf = 2 * 128 * N * 16 / cyc * 148 * 1.9e9 / 1e12
         print("%-6d %8d | %7.1f   %7.0f | %8.1f | %8.1f" % (N, cb, cyc, tf, out[148:].double().mean().item() / tot, (128 + N) * 32 / cyc), flush=True)
 
+print("--- stage-structured issue (wait + fence + elect{MMAs + commit}), 1 vs 2 issuing warps")
+print("%-6s %6s %6s | cycles/MMA  TFLOP/s" % ("N", "MMA/st", "warps"))
+for N in (32, 96, 128, 256):
+    for mps in (4, 12):
+        for nw, bit in ((1, 8), (2, 16)):
+            stages = 9600 // mps
+            out.zero_()
+            L.check(lib.b200unet_umma_rate(N, SW["sw128"], 1024, 1024, 32, mps, stages, 148, out.data_ptr(), None, 0, bit, L.stream_ptr()))
+            torch.cuda.synchronize()
+            cyc = out[:148].double().mean().item() / (mps * stages)
+            print("%-6d %6d %6d | %7.1f   %7.0f" % (N, mps, nw, cyc, 2 * 128 * N * 16 / cyc * 148 * 1.9e9 / 1e12), flush=True)
 print("--- a tcgen05.commit after every `inner` MMAs (pipeline-stage hand-back), sw128 dense")
 print("%-6s %6s | cycles/MMA  TFLOP/s" % ("N", "inner"))
-for N in (32, 64, 96, 128, 256):
-    for inner in (2, 4, 8, 12, 24, 48):
+for mode in (1, 3, 7, 6):
+  print("hand-back mode bits (1 commit, 2 wait, 4 fence):", mode)
+  for N in (32, 96, 128):
+    for inner in (4, 12, 24):
         reps = 9600 // inner
         out.zero_()
-        L.check(lib.b200unet_umma_rate(N, SW["sw128"], 1024, 1024, 32, inner, reps, 148, out.data_ptr(), None, 0, 1, L.stream_ptr()))
+        L.check(lib.b200unet_umma_rate(N, SW["sw128"], 1024, 1024, 32, inner, reps, 148, out.data_ptr(), None, 0, mode, L.stream_ptr()))
         torch.cuda.synchronize()
         cyc = out[:148].double().mean().item() / (inner * reps)
         print("%-6d %6d | %7.1f   %7.0f" % (N, inner, cyc, 2 * 128 * N * 16 / cyc * 148 * 1.9e9 / 1e12), flush=True)
