@@ -55,8 +55,8 @@ __global__ void k_input_pack(const float* __restrict__ x, int C, long long S, Ac
                              int stats_ld) {
   const int n = blockIdx.y;
   const int Cp = out.C;  // 8 or 16
-  __shared__ float s_sum[16][2];
-  if (threadIdx.x < 32) (&s_sum[0][0])[threadIdx.x] = 0.f;
+  __shared__ double s_sum[16][2];   // fp64: the order of the per-warp atomics must not show in the fp32 coefficients
+  if (threadIdx.x < 32) (&s_sum[0][0])[threadIdx.x] = 0.0;
   __syncthreads();
   float acc[16][2];
 #pragma unroll
@@ -82,13 +82,13 @@ __global__ void k_input_pack(const float* __restrict__ x, int C, long long S, Ac
     for (int c = 0; c < 16; ++c) {
       if (c < C) {
         float a = warp_sum(acc[c][0]), b = warp_sum(acc[c][1]);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[c][0], a); atomicAdd(&s_sum[c][1], b); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[c][0], (double)a); atomicAdd(&s_sum[c][1], (double)b); }
       }
     }
     __syncthreads();
     if (threadIdx.x < C) {
-      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x][0]);
-      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 1], (double)s_sum[threadIdx.x][1]);
+      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 0], s_sum[threadIdx.x][0]);
+      atomicAdd(&stats[((long long)n * stats_ld + threadIdx.x) * 2 + 1], s_sum[threadIdx.x][1]);
     }
   }
 }
@@ -125,18 +125,18 @@ __global__ void k_channel_stats(Act x, double* __restrict__ stats, int stats_ld)
       for (int j = 0; j < 8; ++j) { a[j] += v[j]; b[j] += v[j] * v[j]; }
     }
   }
-  extern __shared__ float sm[];  // [C][2]
-  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) sm[i] = 0.f;
+  extern __shared__ double smd[];  // [C][2], fp64 so that the atomic order cannot reach the fp32 coefficients
+  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) smd[i] = 0.0;
   __syncthreads();
   if (vslot < vper) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 0], a[j]);
-      atomicAdd(&sm[(lane_c8 * 8 + j) * 2 + 1], b[j]);
+      atomicAdd(&smd[(lane_c8 * 8 + j) * 2 + 0], (double)a[j]);
+      atomicAdd(&smd[(lane_c8 * 8 + j) * 2 + 1], (double)b[j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], (double)sm[i]);
+  for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], smd[i]);
 }
 
 int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t st) {
@@ -148,7 +148,7 @@ int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t
   int vper = threads / c8n;
   long long want = (S + vper - 1) / vper;
   int blocks = (int)(want < 296 ? want : 296);
-  k_channel_stats<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(float), st>>>(x, stats, stats_ld);
+  k_channel_stats<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(double), st>>>(x, stats, stats_ld);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -238,11 +238,11 @@ static int ew_blocks(long long total, int threads) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-// threads per block: multiple of c8n (and of 32), close to 256
+// threads per block: a multiple of c8n, at most 256 (the kernels' launch bound), a multiple of 32 when one exists
 static int ew_threads_for(int c8n) {
-  int t = 256;
-  while (t % c8n) t += 32;
-  return t;
+  for (int t = 256; t >= 32; t -= 32)
+    if (t % c8n == 0) return t;
+  return c8n <= 256 ? (256 / c8n) * c8n : c8n;
 }
 
 int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st) {
@@ -408,9 +408,9 @@ __device__ __forceinline__ void up_taps(int o, int n, int& i0, int& i1, float& w
 // chunk is constant per thread, so the per-channel statistics accumulate in registers.
 __global__ void __launch_bounds__(256) k_upsample2x_fwd(Act x, Act y, double* __restrict__ stats, int stats_ld) {
   const int c8n = x.C / 8;
-  extern __shared__ float sm[];  // [C][2]
+  extern __shared__ double smu[];  // [C][2], fp64: atomic order must not reach the fp32 coefficients
   if (stats) {
-    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) smu[i] = 0.0;
     __syncthreads();
   }
   const int n = blockIdx.y;
@@ -464,16 +464,16 @@ __global__ void __launch_bounds__(256) k_upsample2x_fwd(Act x, Act y, double* __
           pb += __shfl_xor_sync(0xffffffffu, pb, off);
         }
         if ((threadIdx.x & 31) < c8n) {
-          atomicAdd(&sm[(c8 * 8 + j) * 2 + 0], pa);
-          atomicAdd(&sm[(c8 * 8 + j) * 2 + 1], pb);
+          atomicAdd(&smu[(c8 * 8 + j) * 2 + 0], (double)pa);
+          atomicAdd(&smu[(c8 * 8 + j) * 2 + 1], (double)pb);
         }
       } else {
-        atomicAdd(&sm[(c8 * 8 + j) * 2 + 0], pa);
-        atomicAdd(&sm[(c8 * 8 + j) * 2 + 1], pb);
+        atomicAdd(&smu[(c8 * 8 + j) * 2 + 0], (double)pa);
+        atomicAdd(&smu[(c8 * 8 + j) * 2 + 1], (double)pb);
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], (double)sm[i]);
+    for (int i = threadIdx.x; i < x.C * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * stats_ld * 2 + i], smu[i]);
   }
 }
 
@@ -490,7 +490,7 @@ int launch_upsample2x_fwd(const Act& x, const Act& y, double* stats, int stats_l
   long long want = (nblk + vper - 1) / vper;
   const long long cap = (148LL * 8 + x.N - 1) / x.N;
   const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  k_upsample2x_fwd<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(float), st>>>(x, y, stats, stats_ld);
+  k_upsample2x_fwd<<<dim3(blocks, x.N), threads, x.C * 2 * sizeof(double), st>>>(x, y, stats, stats_ld);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
