@@ -281,12 +281,13 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
               for (int k = 0; k < KC / 16; ++k)
                 umma_bf16(acc0 + (Cfg::STK ? TD - 1 - dpl : dpl) * BN,
                              desc_from(a_lo + ((dpl * 180 * Cfg::RB + k * 32) >> 4), hi_a), desc_from(b_lo0 + ((k * 32) >> 4), hi_b),
-                             idesc, 1u);
+                             idesc, k == 0 ? (first ^ 1u) : 1u);   // first: a lone 1x1x1 convolution starts the tile here
             }
             umma_commit(&b_empty[bs]);
             }
             __syncwarp();
             }
+            first = 0;
             if (++bs == NB) { bs = 0; bph ^= 1; }
           }
           if (elect_one()) umma_commit(&halo_empty[hs]);
@@ -593,6 +594,10 @@ bool conv_halo_eligible(const ConvOp& op) {
   // bound layers); for Cin >= 128 the streaming kernel's deeper K per tile is faster.
   static const int max_c = getenv("B200UNET_HALO_MAXC") ? atoi(getenv("B200UNET_HALO_MAXC")) : 64;
   if (op.src[0].x.C > max_c) return false;
+  // a lone 1x1x1 convolution (the residual blocks' `sample` data gradient) runs as the kernel's centre-tap source: two
+  // MMAs per streaming-kernel tile left that launch bound by per-CTA set-up (0.75 ms for 32->64 at 128^3)
+  static const bool no_1x1 = getenv("B200UNET_NO_HALO_1X1") != nullptr;
+  if (op.nsrc == 1 && op.src[0].ksz == 1 && op.src[0].stride == 1) return !no_1x1 && op.out.W >= 8 && op.out.H >= 16;
   if (op.src[0].ksz != 3 || op.src[0].stride != 1) return false;
   if (op.nsrc == 2 && (op.src[1].ksz != 1 || op.src[1].stride != 1)) return false;
   return op.out.W >= 8 && op.out.H >= 16;
@@ -608,9 +613,16 @@ static bool halo_fits(int KC, int BN, int TD, bool split) {
   return 232448 - 1024 - aux - 2 * halo - 2 * out_buf >= 2 * bbytes;
 }
 
-int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
+int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
+  B200_REQUIRE(conv_halo_eligible(op_in), E_UNSUPPORTED, "conv_halo: shape not eligible");
+  ConvOp op = op_in;
+  const bool only_1x1 = op.nsrc == 1 && op.src[0].ksz == 1;
+  if (only_1x1) {   // centre-tap source lives in slot 1; slot 0 (the 27-tap source) stays empty
+    op.src[1] = op.src[0];
+    op.nsrc = 2;
+  }
+  const int s_begin = only_1x1 ? 1 : 0;
   const Act& out = op.out;
-  B200_REQUIRE(conv_halo_eligible(op), E_UNSUPPORTED, "conv_halo: shape not eligible");
   B200_REQUIRE(out.C % 8 == 0 && out.ld % 8 == 0, E_UNSUPPORTED, "conv_halo: Cout=%d must be a multiple of 8", out.C);
   ConvArgs a;
   memset(&a, 0, sizeof(a));
@@ -619,7 +631,7 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
   a.N = out.N; a.Do = out.D; a.Ho = out.H; a.Wo = out.W; a.Cout = out.C;
   int cin_max = 0;
   bool split = false;
-  for (int s = 0; s < op.nsrc; ++s) {
+  for (int s = s_begin; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
     B200_REQUIRE(c.x.C % 8 == 0 && c.x.ld % 8 == 0, E_UNSUPPORTED, "conv_halo: Cin=%d must be a multiple of 8", c.x.C);
     B200_REQUIRE(c.x.N == out.N && c.x.D == out.D && c.x.H == out.H && c.x.W == out.W, E_INVALID,
@@ -628,7 +640,7 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     if (c.x.lo || c.w_lo) split = true;
   }
   if (split) {
-    for (int s = 0; s < op.nsrc; ++s)
+    for (int s = s_begin; s < op.nsrc; ++s)
       B200_REQUIRE(op.src[s].x.lo && op.src[s].w_lo, E_INVALID, "conv_halo: split mode needs lo parts on every source");
     B200_REQUIRE(out.lo != nullptr, E_INVALID, "conv_halo: split mode needs a lo output");
   }
@@ -658,7 +670,7 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
     if ((v == 1 || v == 2 || v == 3 || v == 6) && ((18 / v) * 10 * KC * 2) % 128 == 0) hsplit = v;
   }
   const int tpb = BN <= 64 ? 3 : 1;
-  for (int s = 0; s < op.nsrc; ++s) {
+  for (int s = s_begin; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = 1;
     a.kchunks[s] = ceil_div(c.x.C, KC);
@@ -674,6 +686,10 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st) {
       if (stk) B200_TRY(make_w_map_kd(&maps.b[s][1], c.w_lo, op.Cop, c.Cip, KC, BN, swz));
       else B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz, boxT));
     }
+  }
+  if (only_1x1) {   // slot 0 is never loaded (kchunks[0] = 0); keep its descriptors valid for the prefetch
+    maps.a[0][0] = maps.a[1][0];
+    maps.b[0][0] = maps.b[1][0];
   }
   // output tile stores: box (min(BN,64) channels, 8, 16, 1, 1), swizzle by the box row bytes
   const int cbo = BN < 64 ? BN : 64;

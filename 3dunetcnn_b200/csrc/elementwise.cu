@@ -156,28 +156,33 @@ int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t
 // ------------------------------------------------------------------------------------------------ GroupNorm finalize
 // stats [N][Ctot][2] (sum, sumsq over the S voxels of each channel) -> coef [N][C][4] = (A, B, mu, rstd):
 //   z = A*x + B  with A = gamma*rstd, B = beta - mu*gamma*rstd ;  xhat = (x - mu)*rstd.    (biased variance, eps)
+// per-channel GroupNorm coefficients (A, B, mu, rstd) from the fp64 (sum, sumsq) statistics: y = A x + B
+__device__ __forceinline__ float4 gn_coef_of(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, int n, int c, int C, int Cld, int G, double S,
+                                             float eps) {
+  if (c >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cg = C / G, g = c / cg;
+  double s = 0, q = 0;
+  for (int j = 0; j < cg; ++j) {
+    s += stats[((long long)n * Cld + g * cg + j) * 2 + 0];
+    q += stats[((long long)n * Cld + g * cg + j) * 2 + 1];
+  }
+  const double m = S * cg;
+  const double mu = s / m;
+  double var = q / m - mu * mu;
+  if (var < 0) var = 0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+  return make_float4((float)(ga * rstd), (float)(be - mu * ga * rstd), (float)mu, (float)rstd);
+}
+
 __global__ void k_gn_finalize(const double* __restrict__ stats, const float* __restrict__ gamma,
                               const float* __restrict__ beta, int C, int Cld, int G, double S, float eps,
                               float4* __restrict__ coef) {
   // C real channels (gamma/beta length); Cld = pitch of stats/coef rows (>= C; padded channels get zero coefs)
   const int n = blockIdx.x;
-  const int cg = C / G;
-  for (int c = threadIdx.x; c < Cld; c += blockDim.x) {
-    if (c >= C) { coef[(long long)n * Cld + c] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-    const int g = c / cg;
-    double s = 0, q = 0;
-    for (int j = 0; j < cg; ++j) {
-      s += stats[((long long)n * Cld + g * cg + j) * 2 + 0];
-      q += stats[((long long)n * Cld + g * cg + j) * 2 + 1];
-    }
-    const double m = S * cg;
-    const double mu = s / m;
-    double var = q / m - mu * mu;
-    if (var < 0) var = 0;
-    const double rstd = 1.0 / sqrt(var + (double)eps);
-    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
-    coef[(long long)n * Cld + c] = make_float4((float)(ga * rstd), (float)(be - mu * ga * rstd), (float)mu, (float)rstd);
-  }
+  for (int c = threadIdx.x; c < Cld; c += blockDim.x)
+    coef[(long long)n * Cld + c] = gn_coef_of(stats, gamma, beta, n, c, C, Cld, G, S, eps);
 }
 
 int launch_gn_finalize(const double* stats, const float* gamma, const float* beta, int N, int C, int Cld, int G,
@@ -191,7 +196,14 @@ int launch_gn_finalize(const double* stats, const float* gamma, const float* bet
 // ------------------------------------------------------------------------------------------------ GroupNorm apply (+ReLU / LeakyReLU)
 // grid (blocks, N); a thread keeps the same 8-channel chunk for its whole grid-stride loop (blockDim.x % c8n == 0),
 // so the affine coefficients live in registers and the loop body is load -> 8 FMA/max -> store, two voxels in flight.
-__global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope) {
+// FUSED: every block first derives the coefficients of its sample from the statistics (a few hundred fp64 loads, hidden
+// behind the other resident blocks) instead of a separate single-block finalize launch per norm layer (~7 us each, 80
+// launches per step); block 0 of each sample also stores them for the backward pass.
+struct GnFin {
+  const double* stats; const float* gamma; const float* beta; int C; int G; double S; float eps; float4* coef_out;
+};
+template <bool FUSED>
+__global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope, GnFin f) {
   const int c8n = x.C / 8;
   const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
@@ -199,10 +211,42 @@ __global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __
   const int vslot = threadIdx.x / c8n;
   const int vper = blockDim.x / c8n;
   float ka[8], kb[8];
+  if constexpr (FUSED) {
+    // one global fp64 load pair per thread, the group sums then come from shared memory (a per-thread loop over the
+    // group's channels in global memory serialised up to 64 L2 latencies in front of every block)
+    __shared__ float2 s_ab[512];
+    __shared__ double s_st[512][2];
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      s_st[c][0] = c < f.C ? f.stats[((long long)n * x.C + c) * 2 + 0] : 0.0;
+      s_st[c][1] = c < f.C ? f.stats[((long long)n * x.C + c) * 2 + 1] : 0.0;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < f.C) {
+        const int cg = f.C / f.G, g = c / cg;
+        double sm_ = 0, q = 0;
+        for (int j = 0; j < cg; ++j) { sm_ += s_st[g * cg + j][0]; q += s_st[g * cg + j][1]; }
+        const double m = f.S * cg;
+        const double mu = sm_ / m;
+        double var = q / m - mu * mu;
+        if (var < 0) var = 0;
+        const double rstd = 1.0 / sqrt(var + (double)f.eps);
+        const double ga = f.gamma ? (double)f.gamma[c] : 1.0, be = f.beta ? (double)f.beta[c] : 0.0;
+        k = make_float4((float)(ga * rstd), (float)(be - mu * ga * rstd), (float)mu, (float)rstd);
+      }
+      s_ab[c] = make_float2(k.x, k.y);
+      if (blockIdx.x == 0) f.coef_out[(long long)n * x.C + c] = k;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
-    ka[j] = k.x; kb[j] = k.y;
+    for (int j = 0; j < 8; ++j) { ka[j] = s_ab[c8 * 8 + j].x; kb[j] = s_ab[c8 * 8 + j].y; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
+      ka[j] = k.x; kb[j] = k.y;
+    }
   }
   const long long base = (long long)n * S;
   const long long stride = (long long)gridDim.x * vper;
@@ -245,19 +289,40 @@ static int ew_threads_for(int c8n) {
   return c8n <= 256 ? (256 / c8n) * c8n : c8n;
 }
 
-int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st) {
+static int launch_gn_apply_impl(const Act& x, const Act& y, const float* coef, float slope, const GnFin* fin, cudaStream_t st) {
   B200_REQUIRE(x.C % 8 == 0 && y.C == x.C, E_INVALID, "gn_apply: C=%d/%d", x.C, y.C);
   const int c8n = x.C / 8;
   const int threads = ew_threads_for(c8n);
-  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "gn_apply: C=%d unsupported", x.C);
+  B200_REQUIRE(threads <= 256, E_UNSUPPORTED, "gn_apply: C=%d unsupported", x.C);
   const long long S = (long long)x.D * x.H * x.W;
   const int vper = threads / c8n;
   long long want = (S + 2LL * vper - 1) / (2LL * vper);
   const long long cap = (148LL * 8 + x.N - 1) / x.N;
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  k_gn_apply<<<dim3(blocks, x.N), threads, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope);
+  if (fin) {
+    B200_REQUIRE(x.C <= 512, E_UNSUPPORTED, "gn_apply: fused finalize supports C <= 512 (got %d)", x.C);
+    k_gn_apply<true><<<dim3(blocks, x.N), threads, 0, st>>>(x, y, nullptr, slope, *fin);
+  } else {
+    GnFin none;
+    memset(&none, 0, sizeof(none));
+    k_gn_apply<false><<<dim3(blocks, x.N), threads, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope, none);
+  }
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
+}
+
+int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st) {
+  return launch_gn_apply_impl(x, y, coef, slope, nullptr, st);
+}
+
+// statistics -> coefficients -> y = relu(A x + B) in one launch; coef_out [N][x.C] float4 is written for the backward pass
+int launch_gn_apply_fused(const Act& x, const Act& y, const double* stats, const float* gamma, const float* beta, int C,
+                          int G, long long S, float eps, float* coef_out, float slope, cudaStream_t st) {
+  B200_REQUIRE(G > 0 && C % G == 0 && C <= x.C, E_INVALID, "gn_apply_fused: C=%d G=%d", C, G);
+  GnFin f;
+  f.stats = stats; f.gamma = gamma; f.beta = beta; f.C = C; f.G = G; f.S = (double)S; f.eps = eps;
+  f.coef_out = reinterpret_cast<float4*>(coef_out);
+  return launch_gn_apply_impl(x, y, nullptr, slope, &f, st);
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm backward
@@ -265,6 +330,25 @@ int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, 
 // coef2 [N][C][2] = (E, F):   dx = A*dz + E*x + F      (A from coef)
 //   c1_g = (1/m) sum_{c in g} gamma_c S1_c ; c2_g = (1/m) sum gamma_c S2_c ; E = -rstd^2 c2 ; F = -rstd c1 + rstd^2 c2 mu
 // dgamma_c = sum_n S2 ; dbeta_c = sum_n S1   (written, not accumulated)
+// (E, F) of dx = A dz + E x + F for channel c of sample n, from the (sum dz, sum dz*xhat) statistics of its group
+__device__ __forceinline__ float2 gn_coef2_of(const double* __restrict__ bstats, const float4* __restrict__ coef,
+                                              const float* __restrict__ gamma, int n, int c, int C, int Cld, int G, double S) {
+  if (c >= C) return make_float2(0.f, 0.f);
+  const int cg = C / G, g = c / cg;
+  double c1 = 0, c2 = 0;
+  for (int j = 0; j < cg; ++j) {
+    const int cc = g * cg + j;
+    const double ga = gamma ? (double)gamma[cc] : 1.0;
+    c1 += ga * bstats[((long long)n * Cld + cc) * 2 + 0];
+    c2 += ga * bstats[((long long)n * Cld + cc) * 2 + 1];
+  }
+  const double m = S * cg;
+  c1 /= m; c2 /= m;
+  const float4 k = coef[(long long)n * Cld + c];
+  const double mu = k.z, rstd = k.w;
+  return make_float2((float)(-rstd * rstd * c2), (float)(-rstd * c1 + rstd * rstd * c2 * mu));
+}
+
 __global__ void k_gn_bwd_finalize(const double* __restrict__ bstats, const float4* __restrict__ coef,
                                   const float* __restrict__ gamma, int N, int C, int Cld, int G, double S,
                                   float2* __restrict__ coef2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -307,9 +391,14 @@ int launch_gn_bwd_finalize(const double* bstats, const float* coef, const float*
 }
 
 // dx = (A*dz + E*x + F (+ add1) (+ add2)) [* scale]     grid (blocks, N), per-thread constant channel chunk
+struct GnBwdFin {
+  const double* bstats; const float* gamma; int C; int G; int N; double S; float* dgamma; float* dbeta;
+};
+// FUSED: the blocks derive (E, F) themselves and block (0, 0) also writes dgamma / dbeta (see k_gn_apply)
+template <bool FUSED>
 __global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef,
                                                 const float2* __restrict__ coef2, Act add1, Act add2, Act dx,
-                                                const float* __restrict__ scale) {
+                                                const float* __restrict__ scale, GnBwdFin f) {
   const int c8n = x.C / 8;
   const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
@@ -317,12 +406,53 @@ __global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __r
   const int vslot = threadIdx.x / c8n;
   const int vper = blockDim.x / c8n;
   float ka[8], ke[8], kf[8], ks[8];
+  if constexpr (FUSED) {
+    __shared__ float2 s_ef[512];
+    __shared__ double s_bs[512][2];   // gamma-weighted backward statistics of every channel of this sample
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      const double ga = (c < f.C && f.gamma) ? (double)f.gamma[c] : 1.0;
+      s_bs[c][0] = c < f.C ? ga * f.bstats[((long long)n * x.C + c) * 2 + 0] : 0.0;
+      s_bs[c][1] = c < f.C ? ga * f.bstats[((long long)n * x.C + c) * 2 + 1] : 0.0;
+      if (blockIdx.x == 0 && n == 0 && c < f.C) {
+        double dg = 0, db = 0;
+        for (int nn = 0; nn < f.N; ++nn) {
+          db += f.bstats[((long long)nn * x.C + c) * 2 + 0];
+          dg += f.bstats[((long long)nn * x.C + c) * 2 + 1];
+        }
+        if (f.dgamma) f.dgamma[c] = (float)dg;
+        if (f.dbeta) f.dbeta[c] = (float)db;
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      float2 e = make_float2(0.f, 0.f);
+      if (c < f.C) {
+        const int cg = f.C / f.G, g = c / cg;
+        double c1 = 0, c2 = 0;
+        for (int j = 0; j < cg; ++j) { c1 += s_bs[g * cg + j][0]; c2 += s_bs[g * cg + j][1]; }
+        const double m = f.S * cg;
+        c1 /= m; c2 /= m;
+        const float4 k = coef[(long long)n * x.C + c];
+        const double mu = k.z, rstd = k.w;
+        e = make_float2((float)(-rstd * rstd * c2), (float)(-rstd * c1 + rstd * rstd * c2 * mu));
+      }
+      s_ef[c] = e;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
-    const float2 e = __ldg(coef2 + (long long)n * x.C + c8 * 8 + j);
-    ka[j] = k.x; ke[j] = e.x; kf[j] = e.y;
-    ks[j] = scale ? __ldg(scale + (long long)n * x.C + c8 * 8 + j) : 1.f;
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = __ldg(coef + (long long)n * x.C + c8 * 8 + j).x;
+      ke[j] = s_ef[c8 * 8 + j].x; kf[j] = s_ef[c8 * 8 + j].y;
+      ks[j] = scale ? __ldg(scale + (long long)n * x.C + c8 * 8 + j) : 1.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 k = __ldg(coef + (long long)n * x.C + c8 * 8 + j);
+      const float2 e = __ldg(coef2 + (long long)n * x.C + c8 * 8 + j);
+      ka[j] = k.x; ke[j] = e.x; kf[j] = e.y;
+      ks[j] = scale ? __ldg(scale + (long long)n * x.C + c8 * 8 + j) : 1.f;
+    }
   }
   const long long base = (long long)n * S;
   const long long stride = (long long)gridDim.x * vper;
@@ -351,23 +481,46 @@ __global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __r
   }
 }
 
-int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1, const Act* add2,
-                  const Act& dx, const float* scale, cudaStream_t st) {
+static int launch_gn_bwd_impl(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1,
+                              const Act* add2, const Act& dx, const float* scale, const GnBwdFin* fin, cudaStream_t st) {
   B200_REQUIRE(x.C % 8 == 0 && dz.C == x.C && dx.C == x.C, E_INVALID, "gn_bwd: channel mismatch");
   Act none = make_act(nullptr, nullptr, 0, 0, 0, 0, 0, 0);
   const int c8n = x.C / 8;
   const int threads = ew_threads_for(c8n);
-  B200_REQUIRE(threads <= 1024, E_UNSUPPORTED, "gn_bwd: C=%d unsupported", x.C);
+  B200_REQUIRE(threads <= 256, E_UNSUPPORTED, "gn_bwd: C=%d unsupported", x.C);
   const long long S = (long long)x.D * x.H * x.W;
   const int vper = threads / c8n;
   long long want = (S + vper - 1) / vper;
   const long long cap = (148LL * 8 + x.N - 1) / x.N;
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  k_gn_bwd<<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
-                                                  reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none,
-                                                  add2 ? *add2 : none, dx, scale);
+  if (fin) {
+    B200_REQUIRE(x.C <= 512, E_UNSUPPORTED, "gn_bwd: fused finalize supports C <= 512 (got %d)", x.C);
+    k_gn_bwd<true><<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef), nullptr,
+                                                          add1 ? *add1 : none, add2 ? *add2 : none, dx, scale, *fin);
+  } else {
+    GnBwdFin nofin;
+    memset(&nofin, 0, sizeof(nofin));
+    k_gn_bwd<false><<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
+                                                           reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none,
+                                                           add2 ? *add2 : none, dx, scale, nofin);
+  }
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
+}
+
+int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1, const Act* add2,
+                  const Act& dx, const float* scale, cudaStream_t st) {
+  return launch_gn_bwd_impl(dz, x, coef, coef2, add1, add2, dx, scale, nullptr, st);
+}
+
+// backward statistics -> (E, F), dgamma, dbeta -> dx = A dz + E x + F (+adds)(*scale) in one launch
+int launch_gn_bwd_fused(const Act& dz, const Act& x, const float* coef, const double* bstats, const float* gamma, int C, int G,
+                        long long S, float* dgamma, float* dbeta, const Act* add1, const Act* add2, const Act& dx,
+                        const float* scale, cudaStream_t st) {
+  B200_REQUIRE(G > 0 && C % G == 0 && C <= x.C, E_INVALID, "gn_bwd_fused: C=%d G=%d", C, G);
+  GnBwdFin f;
+  f.bstats = bstats; f.gamma = gamma; f.C = C; f.G = G; f.N = x.N; f.S = (double)S; f.dgamma = dgamma; f.dbeta = dbeta;
+  return launch_gn_bwd_impl(dz, x, coef, nullptr, add1, add2, dx, scale, &f, st);
 }
 
 // ------------------------------------------------------------------------------------------------ element-wise add (y = a + b)

@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t hi_d = desc_hi(Cfg::SBO, Cfg::LAYOUT);
-      const uint32_t issue = elect_one() ? 1u : 0u;
       const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem0 = smem_u32(smem);
       for (int it = 0; it < total_iters; ++it) {
@@ -135,13 +134,15 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES, 16);
         const uint32_t b_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, 16);
+        if (elect_one()) {   // one elected lane issues the stage (descriptors stay in uniform registers)
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k)
-          umma_bf16_if(issue, tmem0, desc_from(a_lo + 2 * k, hi_d), desc_from(b_lo + 2 * k, hi_d), idesc,
-                       (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit_if(issue, &empty_bar[s]);
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tmem0, desc_from(a_lo + 2 * k, hi_d), desc_from(b_lo + 2 * k, hi_d), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (it == total_iters - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
       }
-      umma_commit_if(issue, tfull_bar);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)

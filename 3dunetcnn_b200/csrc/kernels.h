@@ -10,6 +10,11 @@ int launch_channel_stats(const Act& x, double* stats, int stats_ld, cudaStream_t
 int launch_gn_finalize(const double* stats, const float* gamma, const float* beta, int N, int C, int Cld, int G,
                        long long S, float eps, float* coef, cudaStream_t st);
 int launch_gn_apply(const Act& x, const Act& y, const float* coef, float slope, cudaStream_t st);
+int launch_gn_apply_fused(const Act& x, const Act& y, const double* stats, const float* gamma, const float* beta, int C,
+                          int G, long long S, float eps, float* coef_out, float slope, cudaStream_t st);
+int launch_gn_bwd_fused(const Act& dz, const Act& x, const float* coef, const double* bstats, const float* gamma, int C, int G,
+                        long long S, float* dgamma, float* dbeta, const Act* add1, const Act* add2, const Act& dx,
+                        const float* scale, cudaStream_t st);
 int launch_gn_bwd_finalize(const double* bstats, const float* coef, const float* gamma, int N, int C, int Cld, int G,
                            long long S, float* coef2, float* dgamma, float* dbeta, cudaStream_t st);
 int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* coef2, const Act* add1, const Act* add2,

@@ -322,10 +322,10 @@ static void emit_pack(Plan& P, int ci) {
 static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
   push_op(P.fwd, "gn_apply " + P.norms[ni].name + " " + shape_of(P, x), [&P, ni, x, y](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
-    LAUNCHED(cx, CAT_NORM, launch_gn_finalize(stats_ptr(P, cx, x), cx.params[n.pg], cx.params[n.pb], P.d.batch, n.C, n.Cld, n.G,
-                                    n.S, 1e-5f, reinterpret_cast<float*>(cx.ws + n.coef), cx.st));
-    LAUNCHED(cx, CAT_NORM, launch_gn_apply(act_of(P, cx, x), act_of(P, cx, y), reinterpret_cast<float*>(cx.ws + n.coef), 0.f,
-                                 cx.st));
+    // statistics -> coefficients -> normalise + ReLU in one launch (the coefficients are kept for the backward pass)
+    LAUNCHED(cx, CAT_NORM, launch_gn_apply_fused(act_of(P, cx, x), act_of(P, cx, y), stats_ptr(P, cx, x), cx.params[n.pg],
+                                                 cx.params[n.pb], n.C, n.G, n.S, 1e-5f,
+                                                 reinterpret_cast<float*>(cx.ws + n.coef), 0.f, cx.st));
     return OK;
   });
 }
@@ -435,9 +435,11 @@ static void emit_gn_bwd(Plan& P, int ni, TRef dz, TRef x, TRef add1, TRef dx, bo
     const NormLayer& n = P.norms[ni];
     Act a1;
     if (add1.valid()) a1 = act_of(P, cx, add1);
-    LAUNCHED(cx, CAT_NORM, launch_gn_bwd(act_of(P, cx, dz), act_of(P, cx, x), reinterpret_cast<float*>(cx.ws + n.coef),
-                               reinterpret_cast<float*>(cx.ws + n.coef2), add1.valid() ? &a1 : nullptr, nullptr,
-                               act_of(P, cx, dx), (scale && cx.drop) ? cx.drop : nullptr, cx.st));
+    // finalize fused: (E, F), dgamma, dbeta are derived from the backward statistics inside the kernel
+    LAUNCHED(cx, CAT_NORM, launch_gn_bwd_fused(act_of(P, cx, dz), act_of(P, cx, x), reinterpret_cast<float*>(cx.ws + n.coef),
+                                               reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats), cx.params[n.pg], n.C,
+                                               n.G, n.S, cx.grads[n.pg], cx.grads[n.pb], add1.valid() ? &a1 : nullptr,
+                                               nullptr, act_of(P, cx, dx), (scale && cx.drop) ? cx.drop : nullptr, cx.st));
     return OK;
   });
 }
@@ -479,14 +481,15 @@ static TRef build_block_bwd(Plan& P, const BlockRec& r, TRef dOut) {
   if (r.cs >= 0) emit_wgrad(P, r.cs, r.X, dOut);
   TRef dz2 = full(P, new_buf(P, N, D, H, W, C));
   emit_dgrad(P, r.c2, dOut, dz2, r.n2, r.y1, kNone, false, conv_macs(P, r.c2, dOut));
-  emit_gn_bwd_finalize(P, r.n2);
   TRef dy1 = full(P, new_buf(P, N, D, H, W, C));
   emit_gn_bwd(P, r.n2, dz2, r.y1, kNone, dy1, false);
   emit_wgrad(P, r.c1, r.a1, dy1);
   TRef dz1 = full(P, new_buf(P, N, D, H, W, r.X.c));
   emit_dgrad(P, r.c1, dy1, dz1, r.n1, r.X, kNone, false, r.first ? 0.0 : conv_macs(P, r.c1, dy1));
-  emit_gn_bwd_finalize(P, r.n1);
-  if (r.first) return kNone;
+  if (r.first) {   // no data gradient below the first block: only dgamma / dbeta of its first norm are needed
+    emit_gn_bwd_finalize(P, r.n1);
+    return kNone;
+  }
   TRef dX = full(P, new_buf(P, N, D, H, W, r.X.c));
   if (r.cs >= 0) {
     emit_gn_bwd(P, r.n1, dz1, r.X, kNone, dX, false);

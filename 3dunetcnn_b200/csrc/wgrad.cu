@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
       constexpr uint32_t hi_a = desc_hi(Cfg::SBO_A, Cfg::LAYOUT_A), hi_b = desc_hi(Cfg::SBO_B, Cfg::LAYOUT_B);
-      const uint32_t issue = elect_one() ? 1u : 0u;
       const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t a0 = smem_u32(smem_a), d0s = smem_u32(smem_d);
       int ia = 0, id = 0;
@@ -168,18 +167,22 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
             mbar_wait(&a_full[sa], (ia / WG_A_STAGES) & 1);
             tc_fence_after();
             const uint32_t a_lo = desc_lo(a0 + sa * WG_A_BYTES, Cfg::LBO_A);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16_if(issue, tmem0 + qi * BN, desc_from(a_lo + (k * 2 * Cfg::SBO_A >> 4), hi_a),
-                           desc_from(b_lo + (k * 2 * Cfg::SBO_B >> 4), hi_b), idesc, (k == 0) ? (first ^ 1u) : 1u);
-            umma_commit_if(issue, &a_empty[sa]);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem0 + qi * BN, desc_from(a_lo + (k * 2 * Cfg::SBO_A >> 4), hi_a),
+                          desc_from(b_lo + (k * 2 * Cfg::SBO_B >> 4), hi_b), idesc, (k == 0) ? (first ^ 1u) : 1u);
+              umma_commit(&a_empty[sa]);
+              if (qi == nq - 1) umma_commit(&d_empty[sd]);
+            }
+            __syncwarp();
             ++ia;
           }
-          umma_commit_if(issue, &d_empty[sd]);
           ++id;
         }
       }
-      umma_commit_if(issue, tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else {
     const int lane_base = (warp & 3) * 32;

@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
       constexpr uint32_t hi_a = desc_hi(10 * Cfg::RB, Cfg::LAYOUT_A), hi_b = desc_hi(8 * Cfg::RBN, Cfg::LAYOUT_B);
-      const uint32_t issue = elect_one() ? 1u : 0u;
       const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t h0s = smem_u32(smem_h), d0s = smem_u32(smem_d);
       uint32_t it = 0;
@@ -147,6 +146,7 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
           const uint32_t h_lo = desc_lo(h0s + s * Cfg::HALO_BYTES, Cfg::RB);        // LBO = one voxel row: next kw tap
           const uint32_t d_lo = desc_lo(d0s + s * Cfg::DY_BYTES, Cfg::DY_BOX);
           const uint32_t first = it == 0 ? 1u : 0u;
+          if (elect_one()) {   // one elected lane issues the whole tile pass (descriptors stay in uniform registers)
           for (int qi = 0; qi < nq; ++qi) {
             const int q = q0 + qi;
             const int kd = q / 3, kh = q % 3;
@@ -155,17 +155,20 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
             for (int dpl = 0; dpl < TD; ++dpl) {
 #pragma unroll
               for (int hp = 0; hp < 8; ++hp) {
-                umma_bf16_if(issue, tmem0 + qi * BN, desc_from(a_q + (((dpl * 18 + 2 * hp) * 10) * Cfg::RB >> 4), hi_a),
+                umma_bf16(tmem0 + qi * BN, desc_from(a_q + (((dpl * 18 + 2 * hp) * 10) * Cfg::RB >> 4), hi_a),
                              desc_from(d_lo + (((dpl * 16 + 2 * hp) * 8) * Cfg::RBN >> 4), hi_b), idesc,
                              (dpl == 0 && hp == 0) ? (first ^ 1u) : 1u);
               }
             }
           }
-          umma_commit_if(issue, &h_empty[s]);
-          umma_commit_if(issue, &d_empty[s]);
+          umma_commit(&h_empty[s]);
+          umma_commit(&d_empty[s]);
+          }
+          __syncwarp();
         }
       }
-      umma_commit_if(issue, tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else {
     const int lane_base = (warp & 3) * 32;

@@ -36,6 +36,8 @@ def _packed_to_torch(L, w, mode, split, cout, cin, ksz):
     (32, 32, (8, 16, 16), 3, 1), (64, 32, (4, 16, 8), 3, 1), (8, 32, (16, 16, 16), 3, 1), (128, 128, (8, 16, 8), 3, 1),
     (256, 256, (2, 16, 8), 3, 1), (24, 40, (6, 18, 12), 3, 1), (96, 192, (3, 16, 8), 3, 1), (32, 64, (5, 24, 20), 3, 1),
     (16, 16, (1, 16, 8), 3, 1),
+    # 1x1x1 with a large output plane -> the halo kernel's centre-tap path
+    (32, 64, (4, 16, 8), 1, 1), (8, 32, (5, 18, 12), 1, 1), (64, 32, (2, 16, 16), 1, 1), (24, 40, (3, 16, 9), 1, 1),
 ])
 def test_conv3d_forward(pkg, cin, cout, dims, ksz, stride, split):
     L = pkg.lib
