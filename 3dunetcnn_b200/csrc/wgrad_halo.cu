@@ -10,6 +10,12 @@
 // K = voxels: one MMA contracts 16 voxels = 8(w) x 2(h): the two 8-row K groups are SBO = one halo row (A) / one
 // dense tile row (dY) apart.  Split-K over voxel tiles across CTAs; fp32 vector atomics into dW at the end.
 // Both operands are MN-major; shifted / re-strided descriptors rely on the absolute-address swizzle (probe.cu).
+// The kd taps are stacked along N: halo plane hq (input depth d0-1+hq) meets output plane hq-kd for kd = 0,1,2, i.e. the
+// dY planes hq-2, hq-1, hq, which lie one plane apart in shared memory -- the N swizzle atoms of one MMA (descriptor LBO
+// = one dY plane).  An accumulator is therefore (kc, kh) x [kd = 2,1,0 blocks of BN columns], and one MMA of N = 3*BN
+// (56 cycles at BN = 32) replaces three of N = BN (46 cycles each: the operand-fetch floor of (128 + N) / 4 cycles).
+// The accumulators are zeroed once with tcgen05.st so that every MMA accumulates (an N-stacked MMA cannot overwrite only
+// some of its column blocks).
 #include <cstdlib>
 #include "kernels.h"
 #include "ptx.cuh"
@@ -28,7 +34,7 @@ struct WgHaloArgs {
   int tiles_w, tiles_h, tiles_d, tiles_total;
   int nkc;        // ci chunks
   int gpk;        // accumulator groups per ci chunk
-  int qt;         // accumulators per CTA (<= 9)
+  int qt;         // kh accumulators per CTA (<= 3), each 3*BN columns
   int splits;
   int npass;
   int hsplit;     // halo box loaded as (TD+2)*hsplit TMA boxes, dY tile as TD boxes (more requests in flight)
@@ -72,13 +78,13 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
   // role: blockIdx.y = (kc, group) ; blockIdx.z = co tile ; blockIdx.x = split
   const int kc = blockIdx.y / p.gpk;
   const int grp = blockIdx.y % p.gpk;
-  const int q0 = grp * p.qt;                       // first (kd,kh) index of this CTA
-  const int nq = min(p.qt, 9 - q0);
+  const int q0 = grp * p.qt;                       // first kh of this CTA
+  const int nq = min(p.qt, 3 - q0);
   const int co0 = blockIdx.z * BN;
   const int t0 = (int)((long long)p.tiles_total * blockIdx.x / p.splits);
   const int t1 = (int)((long long)p.tiles_total * (blockIdx.x + 1) / p.splits);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(nq * BN)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(nq * 3 * BN)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
@@ -99,6 +105,13 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {   // zero this warp's lane quadrant of every accumulator column
+    for (int c = 0; c < nq * 3 * BN; c += 16) tmem_zero16(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     {
@@ -132,7 +145,9 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
     }
   } else if (warp == 1) {
     {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * BN, 1, 1);
+      constexpr uint32_t idesc3 = make_idesc_bf16(128, 3 * BN <= 256 ? 3 * BN : BN, 1, 1);
       constexpr uint32_t hi_a = desc_hi(10 * Cfg::RB, Cfg::LAYOUT_A), hi_b = desc_hi(8 * Cfg::RBN, Cfg::LAYOUT_B);
       const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t h0s = smem_u32(smem_h), d0s = smem_u32(smem_d);
@@ -144,25 +159,27 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
           mbar_wait(&d_full[s], ph);
           tc_fence_after();
           const uint32_t h_lo = desc_lo(h0s + s * Cfg::HALO_BYTES, Cfg::RB);        // LBO = one voxel row: next kw tap
-          const uint32_t d_lo = desc_lo(d0s + s * Cfg::DY_BYTES, Cfg::DY_BOX);
-          const uint32_t first = it == 0 ? 1u : 0u;
+          const uint32_t d_lo = desc_lo(d0s + s * Cfg::DY_BYTES, 128 * Cfg::RBN);   // LBO = one dY plane: next kd block
           if (elect_one()) {   // one elected lane issues the whole tile pass (descriptors stay in uniform registers)
-          for (int qi = 0; qi < nq; ++qi) {
-            const int q = q0 + qi;
-            const int kd = q / 3, kh = q % 3;
-            const uint32_t a_q = h_lo + (((kd * 18 + kh) * 10) * Cfg::RB >> 4);
+            for (int qi = 0; qi < nq; ++qi) {
+              const int kh = q0 + qi;
+              const uint32_t a_q = h_lo + ((kh * 10 * Cfg::RB) >> 4);
+              const uint32_t acc = tmem0 + qi * 3 * BN;
 #pragma unroll
-            for (int dpl = 0; dpl < TD; ++dpl) {
+              for (int hq = 0; hq < TD + 2; ++hq) {
+                // halo plane hq pairs with output planes hq - kd, kd in [kdmin, kdmax]; column block (2 - kd), dY plane hq - kd
+                const int kdmin = hq - (TD - 1) > 0 ? hq - (TD - 1) : 0;
+                const int kdmax = hq < 2 ? hq : 2;
+                const int nkd = kdmax - kdmin + 1;
+                const uint32_t idn = nkd == 1 ? idesc1 : nkd == 2 ? idesc2 : idesc3;
 #pragma unroll
-              for (int hp = 0; hp < 8; ++hp) {
-                umma_bf16(tmem0 + qi * BN, desc_from(a_q + (((dpl * 18 + 2 * hp) * 10) * Cfg::RB >> 4), hi_a),
-                             desc_from(d_lo + (((dpl * 16 + 2 * hp) * 8) * Cfg::RBN >> 4), hi_b), idesc,
-                             (dpl == 0 && hp == 0) ? (first ^ 1u) : 1u);
+                for (int hp = 0; hp < 8; ++hp)
+                  umma_bf16(acc + (2 - kdmax) * BN, desc_from(a_q + ((((hq * 18 + 2 * hp) * 10) * Cfg::RB) >> 4), hi_a),
+                            desc_from(d_lo + (((((hq - kdmax) * 16 + 2 * hp) * 8) * Cfg::RBN) >> 4), hi_b), idn, 1u);
               }
             }
-          }
-          umma_commit(&h_empty[s]);
-          umma_commit(&d_empty[s]);
+            umma_commit(&h_empty[s]);
+            umma_commit(&d_empty[s]);
           }
           __syncwarp();
         }
@@ -179,21 +196,23 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
     const int ci = kc * KC + row % KC;
     const bool row_ok = (kw < 3) && (ci < p.Ci) && (t1 > t0);
     for (int qi = 0; qi < nq; ++qi) {
-      const int tap = (q0 + qi) * 3 + kw;
+      for (int blk = 0; blk < 3; ++blk) {
+        const int tap = ((2 - blk) * 3 + (q0 + qi)) * 3 + kw;   // column block blk holds kd = 2 - blk
 #pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + qi * BN + j * 16, r);
-        tmem_ld_wait();
-        const int c = co0 + j * 16;
-        if (row_ok) {
-          float* dst = p.dw + ((long long)tap * p.Cip + ci) * p.Cop + c;
+        for (int j = 0; j < BN / 16; ++j) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + (qi * 3 + blk) * BN + j * 16, r);
+          tmem_ld_wait();
+          const int c = co0 + j * 16;
+          if (row_ok) {
+            float* dst = p.dw + ((long long)tap * p.Cip + ci) * p.Cop + c;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            if (c + i + 3 < p.Cop) {
-              float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                     __uint_as_float(r[i + 3]));
-              atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+            for (int i = 0; i < 16; i += 4) {
+              if (c + i + 3 < p.Cop) {
+                float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                       __uint_as_float(r[i + 3]));
+                atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+              }
             }
           }
         }
@@ -243,17 +262,17 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
   memset(&maps, 0, sizeof(maps));
   const int KC = A.C > 16 ? 32 : 16;
   int BN = Y.C > 32 ? 64 : Y.C > 16 ? 32 : 16;
-  const int TD = 2;
+  const int TD = (BN <= 32 && Y.D >= 4) ? 4 : 2;   // deeper tiles stack more kd taps per MMA (BN = 64: shared memory allows 2)
   const int CBN = BN < 64 ? BN : 64;
   a.N = Y.N; a.D = Y.D; a.H = Y.H; a.W = Y.W;
   a.Ci = A.C; a.Co = Y.C; a.Cip = op.Cip; a.Cop = op.Cop;
   a.tiles_w = ceil_div(Y.W, 8); a.tiles_h = ceil_div(Y.H, 16); a.tiles_d = ceil_div(Y.D, TD);
   a.tiles_total = a.N * a.tiles_d * a.tiles_h * a.tiles_w;
   a.nkc = ceil_div(A.C, KC);
-  a.qt = 512 / BN;
-  if (a.qt > 9) a.qt = 9;
-  a.gpk = ceil_div(9, a.qt);
-  a.qt = ceil_div(9, a.gpk);
+  a.qt = 512 / (3 * BN);   // kh accumulators (3*BN columns each) per CTA
+  if (a.qt > 3) a.qt = 3;
+  a.gpk = ceil_div(3, a.qt);
+  a.qt = ceil_div(3, a.gpk);
   const int cotiles = ceil_div(Y.C, BN);
   const int roles = a.nkc * a.gpk * cotiles;
   int splits = num_sms / roles;
@@ -276,7 +295,8 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
   }
   dim3 grid((unsigned)splits, (unsigned)(a.nkc * a.gpk), (unsigned)cotiles);
 #define B200_WGH_CASE(kc, bn) \
-  if (KC == kc && BN == bn) return launch_wgh<kc, bn, 2>(maps, a, grid, st);
+  if (KC == kc && BN == bn && TD == 2) return launch_wgh<kc, bn, 2>(maps, a, grid, st); \
+  if (KC == kc && BN == bn && TD == 4 && bn <= 32) return launch_wgh<kc, (bn <= 32 ? bn : 32), 4>(maps, a, grid, st);
   B200_WGH_CASE(16, 16) B200_WGH_CASE(16, 32) B200_WGH_CASE(16, 64)
   B200_WGH_CASE(32, 16) B200_WGH_CASE(32, 32) B200_WGH_CASE(32, 64)
 #undef B200_WGH_CASE
