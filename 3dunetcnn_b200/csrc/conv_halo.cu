@@ -590,10 +590,13 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
 }
 
 bool conv_halo_eligible(const ConvOp& op) {
-  // measured on B200 (profiles/r01_convbench.txt): the halo-resident kernel wins for Cin <= 64 (operand-bandwidth
-  // bound layers); for Cin >= 128 the streaming kernel's deeper K per tile is faster.
-  static const int max_c = getenv("B200UNET_HALO_MAXC") ? atoi(getenv("B200UNET_HALO_MAXC")) : 64;
+  // measured on B200 (profiles/r01_convbench.txt): the halo-resident kernel always wins for Cin <= 64.  For wider
+  // inputs both kernels are bound by L2 -> SM operand traffic (the streaming kernel re-reads the activation 27 times);
+  // the halo kernel with 64-channel output tiles and kd-stacked N = 192 MMAs needs about a third of it and wins (1470 vs
+  // 1100 TFLOP/s at 128ch@64^3) once there are enough tiles to fill the SMs: voxels * Cout >= 2^24.
+  static const int max_c = getenv("B200UNET_HALO_MAXC") ? atoi(getenv("B200UNET_HALO_MAXC")) : 512;
   if (op.src[0].x.C > max_c) return false;
+  if (op.src[0].x.C > 64 && (long long)op.out.N * op.out.D * op.out.H * op.out.W * op.out.C < (1LL << 24)) return false;
   // a lone 1x1x1 convolution (the residual blocks' `sample` data gradient) runs as the kernel's centre-tap source: two
   // MMAs per streaming-kernel tile left that launch bound by per-CTA set-up (0.75 ms for 32->64 at 128^3)
   static const bool no_1x1 = getenv("B200UNET_NO_HALO_1X1") != nullptr;
@@ -646,6 +649,7 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   }
   const int KC = cin_max > 16 ? 32 : 16;
   int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
+  if (cin_max > 64 && BN > 64) BN = 64;   // wide inputs: 64-channel tiles so that the kd taps stack to N = 192
   if (const char* e = getenv("B200UNET_HALO_BN")) {   // tuning override: cap the N tile
     const int v = atoi(e);
     if ((v == 16 || v == 32 || v == 64 || v == 128) && v < BN) BN = v;
