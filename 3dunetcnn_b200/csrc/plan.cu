@@ -52,7 +52,9 @@ struct RunCtx {
   const char* label;   // name of the op being launched (profiling only)
 };
 
-enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_NORM, CAT_RESAMPLE, CAT_HEAD, CAT_PACK, CAT_OTHER, CAT_COUNT };
+// CAT_CONV_HALO: forward / data-gradient convolutions that run on the halo-resident kernel (conv_halo.cu); CAT_CONV_FWD and
+// CAT_CONV_DGRAD keep those of the streaming kernel (igemm_conv.cu), so that a per-kernel roofline can be reported
+enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_NORM, CAT_RESAMPLE, CAT_HEAD, CAT_PACK, CAT_OTHER, CAT_CONV_HALO, CAT_COUNT };
 
 struct Prof {
   std::vector<cudaEvent_t> ev;    // 2 per launch
@@ -127,7 +129,7 @@ struct b200unet_plan {
   size_t jobs_off = 0;                           // device copy: pack jobs then unpack jobs
   const void* jobs_uploaded_for = nullptr;       // workspace base the table was last uploaded into
   Prof* prof = nullptr;
-  double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
+  double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
   bool have_drop = false;
   std::vector<size_t> stats_allocs;  // deferred: sizes
@@ -248,6 +250,20 @@ static Act act_of(const Plan& P, const RunCtx& cx, TRef t) {
   return a;
 }
 
+// shape-only copy of the dispatch test (no pointers needed): does this convolution run on the halo-resident kernel?
+static bool goes_halo(const Plan& P, TRef a, int ksz, int stride, bool second_1x1, TRef out) {
+  const Buf& ab = P.bufs[a.buf];
+  const Buf& ob = P.bufs[out.buf];
+  ConvOp op;
+  memset(&op, 0, sizeof(op));
+  op.nsrc = second_1x1 ? 2 : 1;
+  op.src[0].x = make_act(nullptr, nullptr, ab.N, ab.D, ab.H, ab.W, a.c, ab.C);
+  op.src[0].ksz = ksz; op.src[0].stride = stride;
+  if (second_1x1) { op.src[1].ksz = 1; op.src[1].stride = 1; }
+  op.out = make_act(nullptr, nullptr, ob.N, ob.D, ob.H, ob.W, out.c, ob.C);
+  return conv_halo_eligible(op);
+}
+
 static void need_stats(Plan& P, int buf) {
   Buf& b = P.bufs[buf];
   if (b.stats_off >= 0) return;
@@ -339,9 +355,10 @@ static double conv_macs(const Plan& P, int ci, TRef out_like) {
 
 static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, TRef out, bool stats, bool scale) {
   if (stats) need_stats(P, out.buf);
-  P.macs[CAT_CONV_FWD] += conv_macs(P, ci, out) + (ci2 >= 0 ? conv_macs(P, ci2, out) : 0.0);
+ const int cat = goes_halo(P, a, P.convs[ci].ksz, P.convs[ci].stride, ci2 >= 0, out) ? CAT_CONV_HALO : CAT_CONV_FWD;
+  P.macs[cat] += conv_macs(P, ci, out) + (ci2 >= 0 ? conv_macs(P, ci2, out) : 0.0);
   push_op(P.fwd, "conv_fwd " + P.convs[ci].name + " " + shape_of(P, a) + "->" + shape_of(P, out) + (ci2 >= 0 ? " +sample" : "") + (res.valid() ? " +res" : ""),
-          [&P, ci, a, ci2, a2, res, out, stats, scale](RunCtx& cx) -> int {
+          [&P, ci, a, ci2, a2, res, out, stats, scale, cat](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
     memset(&op, 0, sizeof(op));
@@ -365,7 +382,7 @@ static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, T
     if (scale && cx.drop) op.scale = cx.drop;
     if (stats) { op.stats = stats_ptr(P, cx, out); op.stats_ld = P.bufs[out.buf].C; }
     if (c.transposed) { op.bias = cx.params[c.pb]; op.zero_last = 1; }
-    LAUNCHED(cx, CAT_CONV_FWD, launch_igemm_conv(op, cx.st));
+    LAUNCHED(cx, cat, launch_igemm_conv(op, cx.st));
     return OK;
   });
 }
@@ -388,9 +405,10 @@ static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
 // data gradient through conv `ci` (stride 1):  out = conv(dy, Wd)  with either the GN/ReLU backward epilogue
 // (ni >= 0, gn_x = raw input of the norm) or a plain epilogue (+res, *dropout scale).
 static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale, double alg_macs) {
-  P.macs[CAT_CONV_DGRAD] += alg_macs;
+  const int cat = goes_halo(P, dy, P.convs[ci].ksz, P.convs[ci].transposed ? 2 : 1, false, out) ? CAT_CONV_HALO : CAT_CONV_DGRAD;
+  P.macs[cat] += alg_macs;
   push_op(P.bwd, std::string(ni >= 0 ? "dgrad+gnrelu " : "dgrad ") + P.convs[ci].name + " " + shape_of(P, dy) + "->" + shape_of(P, out),
-          [&P, ci, dy, out, ni, gn_x, res, scale](RunCtx& cx) -> int {
+          [&P, ci, dy, out, ni, gn_x, res, scale, cat](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
     memset(&op, 0, sizeof(op));
@@ -414,7 +432,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
       op.slope = 0.f;
       op.bstats = reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats);
     }
-    LAUNCHED(cx, CAT_CONV_DGRAD, launch_igemm_conv(op, cx.st));
+    LAUNCHED(cx, cat, launch_igemm_conv(op, cx.st));
     return OK;
   });
 }

@@ -68,11 +68,11 @@ class _Plan:
     def last_launches(self) -> int:
         return int(self.lib.b200unet_plan_last_launches(self.handle))
 
-    CATEGORIES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "norm_act", "resample", "head", "weight_pack", "other")
+    CATEGORIES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "norm_act", "resample", "head", "weight_pack", "other", "conv_halo")
 
     def algorithmic_macs(self):
-        arr = (C.c_double * 8)()
-        _lib.check(self.lib.b200unet_plan_algorithmic_macs(self.handle, arr, 8), "algorithmic_macs")
+        arr = (C.c_double * 9)()
+        _lib.check(self.lib.b200unet_plan_algorithmic_macs(self.handle, arr, 9), "algorithmic_macs")
         return dict(zip(self.CATEGORIES, [float(v) for v in arr]))
 
     def profile_begin(self, max_launches: int) -> None:
@@ -82,9 +82,9 @@ class _Plan:
         _lib.check(self.lib.b200unet_plan_profile_dump(self.handle, path.encode()), "profile_dump")
 
     def profile_end(self):
-        ms = (C.c_double * 8)()
-        cnt = (C.c_int64 * 8)()
-        _lib.check(self.lib.b200unet_plan_profile_end(self.handle, ms, cnt, 8), "profile_end")
+        ms = (C.c_double * 9)()
+        cnt = (C.c_int64 * 9)()
+        _lib.check(self.lib.b200unet_plan_profile_end(self.handle, ms, cnt, 9), "profile_end")
         return {k: {"ms": float(m), "launches": int(c)} for k, m, c in zip(self.CATEGORIES, ms, cnt)}
 
     def __del__(self):

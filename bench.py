@@ -11,8 +11,9 @@ all-reduce,] fused Adam step.
 
 Prints ONE JSON line on rank 0.  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the
 same step through the reference-facing API (train.batch_loss) from pinned HOST buffers with a loss.item() read-back
-every step.  `roofline`: the implicit-GEMM convolution kernel (forward + data-gradient launches), algorithmic
-FLOPs / CUDA-event time summed over its launches, against the measured bf16 peak.  `cpu_baseline`: the oracle
+every step.  `roofline`: the halo-resident implicit-GEMM convolution kernel k_conv_halo (the forward and data-gradient
+launches it serves; the dominant kernel of the step), algorithmic FLOPs / CUDA-event time summed over its launches,
+against the measured bf16 peak; `traffic` = its DRAM bytes per launch from the committed ncu capture.  `cpu_baseline`: the oracle
 port of the reference model (torch CPU ops, all host threads) on a bounded sample.
 """
 import argparse
@@ -38,6 +39,11 @@ UNIT = "volumes/s"
 
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# mean DRAM bytes per k_conv_halo launch in one C2 training step (ncu, profiles/r01_final_launches.txt); refresh with
+# tools/gpu_trip_prof.sh + tools/summarize_ncu.py when the kernel or the dispatch changes
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 358.5e6
 
 
 def measured_peaks():
@@ -306,10 +312,14 @@ def run_b200_arm(args):
     vols = BATCH_PER_GPU * world * args.steps
     value = vols / (ms_total / 1e3)
     e2e_value = vols / (ms_e2e / 1e3)
-    conv_ms = prof["conv_fwd"]["ms"] + prof["conv_dgrad"]["ms"]
-    conv_launches = prof["conv_fwd"]["launches"] + prof["conv_dgrad"]["launches"]
-    conv_flops = 2.0 * (macs["conv_fwd"] + macs["conv_dgrad"]) * args.steps
+    # dominant kernel: k_conv_halo (forward and data-gradient convolutions on the halo-resident kernel: 42% of the step
+    # in the ncu launch list profiles/r01_final_launches.txt); algorithmic FLOPs of exactly those launches / their time
+    conv_ms = prof["conv_halo"]["ms"]
+    conv_launches = prof["conv_halo"]["launches"]
+    conv_flops = 2.0 * macs["conv_halo"] * args.steps
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    all_conv_ms = sum(prof[k]["ms"] for k in ("conv_halo", "conv_fwd", "conv_dgrad", "conv_wgrad"))
+    all_conv_flops = 2.0 * sum(macs[k] for k in ("conv_halo", "conv_fwd", "conv_dgrad", "conv_wgrad")) * args.steps
     kernels = {}
     for k, v in prof.items():
         if v["launches"]:
@@ -330,8 +340,11 @@ def run_b200_arm(args):
                 "api": "train.batch_loss(model, images, target, criterion) + backward + Adam; pinned host buffers, H2D on a copy stream"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "k_igemm_conv (forward + data-gradient launches)", "achieved": achieved,
-                     "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "k_conv_halo (halo-resident implicit-GEMM conv: forward + data-gradient launches)",
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                     # DRAM bytes per launch (read + write) of the same kernel, ncu capture profiles/r01_final_launches.txt
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_final_launches.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the kernel's launches of one step)",
+                     "all_conv_kernels_tflops": all_conv_flops / (all_conv_ms / 1e3) / 1e12 if all_conv_ms > 0 else 0.0,
                      "launches_per_step": conv_launches / args.steps, "ms_per_step": conv_ms / args.steps,
                      "peak_source": peaks["source"],
                      "timing": "CUDA-event pair around every launch on the launching stream, K steps repeated after the timed region",

@@ -17,30 +17,45 @@ METRICS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_p
 
 
 def launches(src, dst):
+    """Launch list of one warm step: time share per kernel and, when the capture has them, DRAM bytes per launch."""
     lines = [l for l in open(src) if l.startswith('"')]
     r = csv.reader(lines)
     hdr = next(r)
     idx = {h: i for i, h in enumerate(hdr)}
     data = [row for row in r if len(row) == len(hdr)]
-    names = [d[idx["Kernel Name"]] for d in data]
-    starts = [i for i, n in enumerate(names) if "k_input_pack" in n]
-    seg = data[starts[-1]:] if starts else data          # the last (warm) step
-    tot = collections.defaultdict(lambda: [0, 0.0])
-    for d in seg:
-        name = re.sub(r"\(.*", "", d[idx["Kernel Name"]]).replace("void ", "")
+    # one record per launch ID: {metric: value}
+    recs = collections.OrderedDict()
+    for d in data:
+        key = d[idx["ID"]]
+        rec = recs.setdefault(key, {"name": d[idx["Kernel Name"]]})
         v = float(d[idx["Metric Value"]].replace(",", ""))
         unit = d[idx["Metric Unit"]]
-        v = v / 1e6 if unit == "ns" else v / 1e3 if unit == "us" else v * 1e3 if unit == "s" else v
+        m = d[idx["Metric Name"]]
+        if m == "gpu__time_duration.sum":
+            v = v / 1e6 if unit == "ns" else v / 1e3 if unit == "us" else v * 1e3 if unit == "s" else v   # -> ms
+        else:
+            v = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        rec[m] = v
+    recs = list(recs.values())
+    starts = [i for i, r_ in enumerate(recs) if "k_input_pack" in r_["name"]]
+    # the last COMPLETE step: from the second-to-last k_input_pack to the last one (the capture may end mid-step)
+    seg = recs[starts[-2]:starts[-1]] if len(starts) >= 2 else recs
+    tot = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r_ in seg:
+        name = re.sub(r"\(.*", "", r_["name"]).replace("void ", "")
+        name = re.sub(r"<.*", "", name)
         tot[name][0] += 1
-        tot[name][1] += v
-    s = sum(v[1] for v in tot.values())
+        tot[name][1] += r_.get("gpu__time_duration.sum", 0.0)
+        tot[name][2] += r_.get("dram__bytes_read.sum", 0.0) + r_.get("dram__bytes_write.sum", 0.0)
+    s_ = sum(v[1] for v in tot.values())
     with open(dst, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none : last training step of tools/prof_step.py\n")
-        f.write("# (cold-cache, serialised per-launch times: compare SHARES, not absolutes)\n")
-        f.write("%-64s %6s %10s %7s\n" % ("kernel", "n", "ms", "share"))
+        f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none :\n")
+        f.write("# one warm training step of `python bench.py` (cold-cache, serialised per-launch times: compare SHARES)\n")
+        f.write("%-40s %6s %10s %7s %14s %12s\n" % ("kernel", "n", "ms", "share", "DRAM MB/launch", "DRAM GB/s"))
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-            f.write("%-64s %6d %10.3f %6.1f%%\n" % (k[:64], v[0], v[1], 100 * v[1] / s))
-        f.write("%-64s %6d %10.3f\n" % ("TOTAL", sum(v[0] for v in tot.values()), s))
+            f.write("%-40s %6d %10.3f %6.1f%% %14.1f %12.0f\n" % (k[:40], v[0], v[1], 100 * v[1] / s_, v[2] / v[0] / 1e6,
+                                                               v[2] / (v[1] / 1e3) / 1e9 if v[1] else 0))
+        f.write("%-40s %6d %10.3f\n" % ("TOTAL", sum(v[0] for v in tot.values()), s_))
     print(open(dst).read())
 
 
