@@ -590,7 +590,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
 }
 
 bool conv_halo_eligible(const ConvOp& op) {
-  // measured on B200 (profiles/r01_convbench.txt): the halo-resident kernel always wins for Cin <= 64.  For wider
+  // measured on B200 (profiles/r01_final_convbench.jsonl): the halo-resident kernel always wins for Cin <= 64.  For wider
   // inputs both kernels are bound by L2 -> SM operand traffic (the streaming kernel re-reads the activation 27 times);
   // the halo kernel with 64-channel output tiles and kd-stacked N = 192 MMAs needs about a third of it and wins (1470 vs
   // 1100 TFLOP/s at 128ch@64^3) once there are enough tiles to fill the SMs: voxels * Cout >= 2^24.
