@@ -596,7 +596,9 @@ bool conv_halo_eligible(const ConvOp& op) {
   // 1100 TFLOP/s at 128ch@64^3) once there are enough tiles to fill the SMs: voxels * Cout >= 2^24.
   static const int max_c = getenv("B200UNET_HALO_MAXC") ? atoi(getenv("B200UNET_HALO_MAXC")) : 512;
   if (op.src[0].x.C > max_c) return false;
-  if (op.src[0].x.C > 64 && (long long)op.out.N * op.out.D * op.out.H * op.out.W * op.out.C < (1LL << 24)) return false;
+  long long wide_min = 1LL << 24;   // tests lower it (B200UNET_HALO_WIDE_MIN=0) to reach this path with small oracle-sized shapes
+  if (const char* e = getenv("B200UNET_HALO_WIDE_MIN")) wide_min = atoll(e);
+  if (op.src[0].x.C > 64 && (long long)op.out.N * op.out.D * op.out.H * op.out.W * op.out.C < wide_min) return false;
   // a lone 1x1x1 convolution (the residual blocks' `sample` data gradient) runs as the kernel's centre-tap source: two
   // MMAs per streaming-kernel tile left that launch bound by per-CTA set-up (0.75 ms for 32->64 at 128^3)
   static const bool no_1x1 = getenv("B200UNET_NO_HALO_1X1") != nullptr;
