@@ -1,22 +1,24 @@
-// Halo-resident implicit-GEMM convolution (3x3x3, stride 1) for sm_100a: the successor of igemm_conv.cu's per-tap
-// streaming kernel for the operand-bandwidth-bound layers (Cin <= 64) whose output plane is at least 8 x 16.
+// Halo-resident implicit-GEMM convolution (3x3x3 stride 1, optional fused 1x1x1 second source, or a lone 1x1x1) for
+// sm_100a: the dominant kernel of the training step.  Used whenever the output plane is at least 8 x 16 and either
+// Cin <= 64 or there are enough tiles (see conv_halo_eligible); igemm_conv.cu's per-tap streaming kernel takes the rest.
 //
-// A CTA (persistent, one per SM) walks output tiles of 8(w) x 16(h) x TD(d) voxels.  For each K chunk of KC input
-// channels it TMA-loads ONE halo box (KC, 10, 18, TD+2) of the activation into shared memory and serves all 27 taps
-// from it: tap (kd,kh,kw) of output plane d is the UMMA A operand whose descriptor START ADDRESS is shifted by
+// A CTA (persistent, one per SM) walks output tiles of 8(w) x 16(h) x TD(d) voxels x BN channels.  For each K chunk of
+// KC input channels it TMA-loads ONE halo box (KC, 10, 18, TD+2) of the activation into shared memory and serves all 27
+// taps from it: tap (kd,kh,kw) of output plane d is the UMMA A operand whose descriptor START ADDRESS is shifted by
 // ((d+kd)*18 + kh)*10 + kw rows and whose 8-row-group stride (SBO) is one halo row of 10 voxels.  The hardware applies
 // the 64B/32B swizzle on absolute shared-memory address bits (verified by csrc/probe.cu on B200, profiles/probe_r01.txt),
 // so shifted / re-strided descriptors read exactly what TMA wrote.  L2->SM activation traffic drops from 27 reads per
 // voxel (streaming kernel) to (TD+2)/TD * 1.41.
-// Weights stream through a ring in groups of TPB taps (one TMA box, one barrier round-trip per group: the per-tap
-// handshake cost ~200 cycles, measured with the HALO_STAMP timeline); each weight tile is reused by TD output planes,
-// i.e. TD accumulators of 128 x BN fp32 live in TMEM, in NACC sets so the epilogue of tile i overlaps the MMAs of
-// tile i+1; two halo buffers let the next chunk / tile load under the current MMAs.
-// Issue loops are warp-convergent with one elected lane issuing (descriptors stay in uniform registers).
-// Epilogue (4 warps): TMEM -> registers -> (+residual)(*dropout)(+bias) | GroupNorm/ReLU backward -> swizzled shared
-// staging tile -> TMA store (full-line writes; the per-thread 16-byte global stores of the first version cost ~40
-// cycles per touched line and bounded every narrow layer).  Per-channel statistics accumulate in registers across
-// planes and tiles (BN <= 64) and are reduced by a transposing warp butterfly only when the sample changes.
+// Weights stream through a ring of stages; for BN <= 64 a stage holds the kd = 0,1,2 tiles of one (kh,kw) and the MMAs
+// are stacked along N (one MMA of N = 3*BN feeds three output planes: see the issuer).  TD accumulators of 128 x BN fp32
+// live in TMEM, in NACC sets so the epilogue of tile i overlaps the MMAs of tile i+1; two halo buffers let the next
+// chunk / tile load under the current MMAs.
+// Warps: 0 = weight-stage producer, 10 = halo producer, 1 = MMA issuer (one elected lane per stage), 2..9 = epilogue in
+// two groups of four.  Epilogue: TMEM -> registers -> (+residual)(*dropout)(+bias) | GroupNorm/ReLU backward -> swizzled
+// shared staging tile -> TMA store (full-line writes; the per-thread 16-byte global stores of the first version cost
+// ~40 cycles per touched line and bounded every narrow layer).  Per-channel statistics accumulate in registers across
+// planes and tiles (BN <= 64) and are reduced by a transposing warp butterfly only when the sample changes; their
+// reduction order is fixed, so repeated launches give bit-identical statistics up to the final fp64 atomics.
 #include <cstdlib>
 #include "conv_common.cuh"
 
