@@ -24,7 +24,9 @@
 
 namespace b200 {
 
-template <int KC, int BN, int TD>
+// NI = number of MMA-issuing warps (1, or 2 = experimental: each issuer accumulates its stages into its OWN accumulator
+// set and the epilogue adds the two; BN <= 32 only, enabled with B200UNET_HALO_ISSUERS=2)
+template <int KC, int BN, int TD, int NI = 1>
 struct HaloCfg {
   static constexpr int RB = KC * 2;                         // bytes per voxel row of the halo
   static constexpr int HALO_ROWS = 180 * (TD + 2);          // 10 x 18 x (TD+2)
@@ -40,8 +42,9 @@ struct HaloCfg {
   static constexpr int NBO = BN / CBO;
   static constexpr int OUT_BOX = 128 * CBO * 2;
   static constexpr int OUT_TILE = 128 * BN * 2;             // one plane, one of {hi, lo}
-  static constexpr int NACC = (2 * TD * BN <= 512) ? 2 : 1;
-  static constexpr int ACC_COLS = NACC * TD * BN;
+  static constexpr int NACC = (2 * NI * TD * BN <= 512) ? 2 : 1;
+  static constexpr int ACC_COLS = NACC * NI * TD * BN;
+  static_assert(NI == 1 || NI == 2, "one or two issuing warps");
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int AUX_BYTES = 1024 + 8 * BN * 2 * 4 + BN * 16;   // barriers | per-warp stats | GN coefficients
   static constexpr int BUDGET = 232448 - 1024;                   // dynamic smem limit minus alignment slack
@@ -69,10 +72,10 @@ struct HaloArgs {
 #define HALO_STAMP(role, slot) \
   do { if (hp.dbg && blockIdx.x == 0 && ti < 32 && lane == 0) hp.dbg[((role) * 32 + ti) * 4 + (slot)] = clock64(); } while (0)
 
-template <int KC, int BN, int TD>
-__global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
-                                                      const HaloArgs hp) {
-  using Cfg = HaloCfg<KC, BN, TD>;
+template <int KC, int BN, int TD, int NI = 1>
+__global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
+                                                                      const HaloArgs hp) {
+  using Cfg = HaloCfg<KC, BN, TD, NI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int out_buf_bytes = Cfg::OUT_TILE * (hp.split ? 2 : 1);
@@ -101,9 +104,9 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
+      for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], NI); }
       for (int s = 0; s < Cfg::NB_MAX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-      for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+      for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], NI); mbar_init(&acc_empty[s], 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -169,18 +172,19 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one warp, one elected lane per stage)
+  } else if (warp == 1 || (NI == 2 && warp == 11)) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane per stage)
     // tcgen05.mma issue is the critical path once the MMAs run near their operand-fetch bound of (128 + N) / 4 cycles:
     // a UTCHMMA holds its uniform-register operands until the tensor pipe dequeues it, so the wait / fence / descriptor
     // set-up of the next stage cannot run ahead (tools/umma_rate.py: one issuing warp reaches 95 cycles per N=128 MMA at
     // 4 MMAs per stage, 76 at 12).  Two issuing warps alternating stages reach the bound in the micro-benchmark, but
     // MMAs of DIFFERENT threads accumulating into the same TMEM columns are not ordered: tools/conv_determinism.py
-    // showed lost updates (thousands of elements differing run to run), so a single thread issues every MMA of a tile.
-    // The single issuing warp is the critical resource once the MMAs run near their operand-fetch bound of
-    // (128 + N) / 4 cycles (tools/umma_rate.py): the stage loop is fully unrolled so that every tap / plane / k offset
-    // is an immediate added to a uniform base, and the weight-ring slot and phase are carried instead of recomputed
-    // with div/mod -- the rolled loop spent ~70 instructions per 4-MMA stage and ran the wide layers at 108 cycles/MMA.
+    // showed lost updates (thousands of elements differing run to run), so with NI = 1 a single thread issues every MMA
+    // of a tile.  NI = 2 (experimental): warp `iw` owns the stages of parity iw and accumulates them into its own
+    // accumulator set; no column is ever written by two threads and the epilogue adds the two sets.
+    // The stage loop is rolled with incremental tap offsets (a 27-stage unrolled body thrashed the instruction cache);
+    // the weight-ring slot and phase are carried instead of recomputed with div/mod.
+    const uint32_t iw = (NI == 2 && warp == 11) ? 1u : 0u;
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t idesc2 = make_idesc_bf16(128, BN * 2 <= 256 ? BN * 2 : BN, 0, 0);
     constexpr uint32_t idesc3 = make_idesc_bf16(128, BN * 3 <= 256 ? BN * 3 : BN, 0, 0);
@@ -191,17 +195,17 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
     uint32_t hs = 0, hph = 0, bs = 0, bph = 0, ti = 0;   // halo / weight ring slot and phase
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       const uint32_t as = ti % Cfg::NACC;
-      HALO_STAMP(1, 0);
+      if (iw == 0) HALO_STAMP(1, 0);
       mbar_wait(&acc_empty[as], ((ti / Cfg::NACC) & 1) ^ 1);
       tc_fence_after();
-      HALO_STAMP(1, 1);
-      const uint32_t acc0 = tmem0 + as * TD * BN;
-      uint32_t first = 1;
+      if (iw == 0) HALO_STAMP(1, 1);
+      const uint32_t acc0 = tmem0 + (as * NI + iw) * TD * BN;
+      uint32_t first = 1, sidx = 0;   // first: this warp has not issued into its accumulator set yet; sidx: stage index in the tile
       for (int g = 0; g < groups0 + groups1; ++g) {
         const int src = g < groups0 ? 0 : 1;
         for (int pass = 0; pass < p.npass; ++pass) {
           mbar_wait(&halo_full[hs], hph);
-          HALO_STAMP(1, 2);
+          if (iw == 0) HALO_STAMP(1, 2);
           const uint32_t halo_lo = desc_lo(halo0 + hs * Cfg::HALO_BYTES, 16);
           if (src == 0) {
             // rolled on purpose: the 27-stage unrolled body (~4K instructions) thrashed the instruction cache
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
             int kw = 0, kh = 0;
 #pragma unroll 1
             for (int st = 0; st < STAGES0; ++st) {
-              {
+              if (NI == 1 || ((sidx + st) & 1u) == iw) {
                 mbar_wait(&b_full[bs], bph);
                 tc_fence_after();
                 const uint32_t b_lo0 = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
@@ -258,8 +262,8 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
                   umma_commit(&b_empty[bs]);
                 }
                 __syncwarp();
+                first = 0;
               }
-              first = 0;
               if (++bs == NB) { bs = 0; bph ^= 1; }
               // next tap: kw fastest, then kh, (then kd for unstacked stages)
               a_off += Cfg::RB >> 4;
@@ -269,9 +273,10 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
                 if (++kh == 3) { kh = 0; a_off += (15 * 10 * Cfg::RB) >> 4; }
               }
             }
+            sidx += STAGES0;
           } else {
             // fused 1x1x1 source: one stage holding its only tap, read at the halo centre (kd = kh = kw = 1)
-            {
+            if (NI == 1 || (sidx & 1u) == iw) {
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
             const uint32_t b_lo0 = desc_lo(b0 + bs * Cfg::B_BYTES, 16);
@@ -288,8 +293,9 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
             umma_commit(&b_empty[bs]);
             }
             __syncwarp();
-            }
             first = 0;
+            }
+            ++sidx;
             if (++bs == NB) { bs = 0; bph ^= 1; }
           }
           if (elect_one()) umma_commit(&halo_empty[hs]);
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
       }
       if (elect_one()) umma_commit(&acc_full[as]);
       __syncwarp();
-      HALO_STAMP(1, 3);
+      if (iw == 0) HALO_STAMP(1, 3);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -442,7 +448,15 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
           float* aq_ = rq + (RUN ? jj * 16 : 0);
           if (c0 < p.Cout) {
             uint32_t r[16];
-            tmem_ld16(tmem_base + (as * TD + (Cfg::STK ? TD - 1 - dpl : dpl)) * BN + (static_cast<uint32_t>(lane_base) << 16) + j * 16, r);
+            const uint32_t tcol = (as * NI * TD + (Cfg::STK ? TD - 1 - dpl : dpl)) * BN + j * 16;
+            tmem_ld16(tmem_base + tcol + (static_cast<uint32_t>(lane_base) << 16), r);
+            if constexpr (NI == 2) {   // the second issuer's partial sums live TD planes further
+              uint32_t r2[16];
+              tmem_ld16(tmem_base + tcol + TD * BN + (static_cast<uint32_t>(lane_base) << 16), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -561,9 +575,9 @@ __global__ void __launch_bounds__(352, 1) k_conv_halo(const __grid_constant__ Co
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int KC, int BN, int TD>
+template <int KC, int BN, int TD, int NI = 1>
 static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, int grid, cudaStream_t st) {
-  using Cfg = HaloCfg<KC, BN, TD>;
+  using Cfg = HaloCfg<KC, BN, TD, NI>;
   // shared-memory carve-up: 2 halo buffers | nout output staging buffers | weight ring | aux
   const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
@@ -583,10 +597,10 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD><<<grid, 352, smem_bytes, st>>>(maps, a, h);
+  k_conv_halo<KC, BN, TD, NI><<<grid, NI == 2 ? 384 : 352, smem_bytes, st>>>(maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -730,6 +744,18 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);
   const int grid = h.tiles_total < num_sms ? h.tiles_total : num_sms;
+  // experimental: two issuing warps with private accumulator sets (BN <= 32, at least two weight stages per tile)
+  static const bool two_issuers = getenv("B200UNET_HALO_ISSUERS") && atoi(getenv("B200UNET_HALO_ISSUERS")) == 2;
+  const int stages_per_tile = (a.kchunks[0] * (BN <= 64 ? 9 : 27) + (a.ntaps[1] ? a.kchunks[1] : 0)) * a.npass;
+  if (two_issuers && BN <= 32 && stages_per_tile >= 2) {
+#define B200_HALO_CASE2(kc, bn, td) \
+  if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td, 2>(maps, a, h, grid, st);
+    B200_HALO_CASE2(16, 16, 4) B200_HALO_CASE2(16, 16, 2) B200_HALO_CASE2(16, 16, 1)
+    B200_HALO_CASE2(16, 32, 4) B200_HALO_CASE2(16, 32, 2) B200_HALO_CASE2(16, 32, 1)
+    B200_HALO_CASE2(32, 16, 4) B200_HALO_CASE2(32, 16, 2) B200_HALO_CASE2(32, 16, 1)
+    B200_HALO_CASE2(32, 32, 4) B200_HALO_CASE2(32, 32, 2) B200_HALO_CASE2(32, 32, 1)
+#undef B200_HALO_CASE2
+  }
 #define B200_HALO_CASE(kc, bn, td) \
   if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td>(maps, a, h, grid, st);
   B200_HALO_CASE(16, 16, 4) B200_HALO_CASE(16, 16, 2) B200_HALO_CASE(16, 16, 1)
