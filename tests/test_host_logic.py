@@ -129,3 +129,61 @@ def test_epoch_training_plumbing_cpu(pkg):
     assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
     v = pkg.train.epoch_validation(loader, model, Crit(), n_gpus=None)
     assert 0 < v < 1
+
+
+# ------------------------------------------------------------------------------------------------ kernel index arithmetic
+# Executable restatement of the stacked-MMA bookkeeping of csrc/conv_halo.cu and csrc/wgrad_halo.cu: every (output plane,
+# kd tap) pair must be produced exactly once, into the accumulator columns the epilogue later reads.
+@pytest.mark.parametrize("TD", [1, 2, 4])
+def test_conv_halo_kd_stacking_covers_every_plane_tap_pair_once(TD):
+    seen = {}
+    for hq in range(TD + 2):                                   # halo plane = input depth d0 - 1 + hq
+        kdmin = max(0, hq - (TD - 1))
+        kdmax = min(2, hq)
+        nkd = kdmax - kdmin + 1
+        assert 1 <= nkd <= 3
+        d_slot0 = TD - 1 - hq + kdmin                          # accumulators sit in DESCENDING plane order (units of BN)
+        assert 0 <= d_slot0 and d_slot0 + nkd <= TD            # the N-stacked MMA stays inside the tile's accumulators
+        for j in range(nkd):
+            kd = kdmin + j                                     # weight row block kdmin + j  <->  column block d_slot0 + j
+            plane = TD - 1 - (d_slot0 + j)
+            assert plane == hq - kd                            # tap kd of output plane p reads halo plane p + kd
+            assert (plane, kd) not in seen
+            seen[(plane, kd)] = hq
+    assert sorted(seen) == [(p, kd) for p in range(TD) for kd in range(3)]
+
+
+@pytest.mark.parametrize("TD", [2, 4])
+def test_wgrad_halo_kd_stacking_pairs_each_halo_plane_with_the_right_dy_planes(TD):
+    seen = set()
+    for hq in range(TD + 2):
+        kdmin = max(0, hq - (TD - 1))
+        kdmax = min(2, hq)
+        nkd = kdmax - kdmin + 1
+        blk0 = 2 - kdmax                                       # column block b holds kd = 2 - b
+        dy0 = hq - kdmax                                       # first dY plane of the N atoms (ascending addresses)
+        assert 0 <= dy0 and dy0 + nkd <= TD and 0 <= blk0 and blk0 + nkd <= 3
+        for j in range(nkd):
+            kd = 2 - (blk0 + j)
+            assert dy0 + j == hq - kd                          # dY plane d pairs with input plane d + kd
+            seen.add((dy0 + j, kd))
+    assert seen == {(p, kd) for p in range(TD) for kd in range(3)}
+
+
+@pytest.mark.parametrize("stacked", [True, False])
+def test_conv_halo_incremental_tap_offsets(stacked):
+    """the rolled stage loop advances the A-descriptor offset incrementally (kw fastest, then kh, then kd)"""
+    rb = 4                                                     # halo row bytes >> 4 for KC = 32
+    a_off, kw, kh = 0, 0, 0
+    for st in range(9 if stacked else 27):
+        kd_, kh_, kw_ = (0, st // 3, st % 3) if stacked else (st // 9, (st // 3) % 3, st % 3)
+        assert a_off == ((kd_ * 18 + kh_) * 10 + kw_) * rb
+        a_off += rb
+        kw += 1
+        if kw == 3:
+            kw = 0
+            a_off += 7 * rb
+            kh += 1
+            if kh == 3:
+                kh = 0
+                a_off += 15 * 10 * rb
