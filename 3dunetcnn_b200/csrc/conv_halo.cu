@@ -585,8 +585,8 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   h.nout = Cfg::COLSPLIT ? 2 : (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;
   if (const char* e = getenv("B200UNET_HALO_NOUT")) {   // tuning override
     const int v = atoi(e);
-    if ((v == 2 || v == 4) && (Cfg::COLSPLIT || v == 4 || true)) h.nout = Cfg::COLSPLIT ? 2 : v;
-    if (v == 1 && Cfg::COLSPLIT) h.nout = 1;
+    if (Cfg::COLSPLIT) { if (v == 1 || v == 2) h.nout = v; }   // shared ring of 1 or 2
+    else if (v == 2 || v == 4) h.nout = v;                      // 1 or 2 per plane-split group
   }
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
