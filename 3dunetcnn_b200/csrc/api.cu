@@ -4,6 +4,7 @@
 
 #include "kernels.h"
 #include "../../include/b200unet.h"
+#include "../../include/b200unet_diag.h"
 
 namespace b200 {
 static thread_local char g_err[1024] = "";

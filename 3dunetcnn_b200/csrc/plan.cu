@@ -330,11 +330,7 @@ static std::string shape_of(const Plan& P, TRef t) {
   return std::to_string(t.c) + "ch@" + std::to_string(b.D) + "x" + std::to_string(b.H) + "x" + std::to_string(b.W);
 }
 
-// ---- forward op emitters
-static void emit_pack(Plan& P, int ci) {
-  (void)P; (void)ci;   // packing is batched: see the k_pack_all launch at the head of the forward schedule
-}
-
+// ---- forward op emitters (weight packing is batched: see the k_pack_all launch at the head of the forward schedule)
 static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
   push_op(P.fwd, "gn_apply " + P.norms[ni].name + " " + shape_of(P, x), [&P, ni, x, y](RunCtx& cx) -> int {
     const NormLayer& n = P.norms[ni];
@@ -479,9 +475,6 @@ static BlockRec build_block_fwd(Plan& P, const std::string& pre, TRef X, int cin
   r.y1 = full(P, new_buf(P, N, D, H, W, C));
   r.a2 = full(P, new_buf(P, N, D, H, W, C));
   r.out = dest;
-  emit_pack(P, r.c1);
-  emit_pack(P, r.c2);
-  if (r.cs >= 0) emit_pack(P, r.cs);
   emit_norm_fwd(P, r.n1, X, r.a1);
   emit_conv_fwd(P, r.c1, r.a1, -1, kNone, kNone, r.y1, true, false);
   emit_norm_fwd(P, r.n2, r.y1, r.a2);
@@ -594,7 +587,6 @@ static int build(Plan& P) {
     skip[li] = X;
     if (li + 1 < L) {
       down[li] = new_conv(P, "encoder.downsampling_convolutions." + std::to_string(li) + ".weight", C, C, 3, 2, true);
-      emit_pack(P, down[li]);
       down_out[li] = full(P, new_buf(P, N, Ds[li + 1], Hs[li + 1], Ws[li + 1], C));
       emit_conv_fwd(P, down[li], X, -1, kNone, kNone, down_out[li], true, false);
       X = down_out[li];
@@ -622,7 +614,6 @@ static int build(Plan& P) {
     s.cpre = -1; s.cup = -1; s.P = kNone; s.Z = kNone;
     if (!d.use_transposed_convolutions) {
       s.cpre = new_conv(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", out_w, in_w, 1, 1, true);
-      emit_pack(P, s.cpre);
       s.P = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
       emit_conv_fwd(P, s.cpre, X, -1, kNone, kNone, s.P, false, false);
       TRef Pin = s.P, U = s.U;

@@ -74,8 +74,6 @@ _SIGS = {
     "b200unet_conv3d": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "b200unet_conv3d_wgrad": (C.c_int, [C.POINTER(Tensor5), C.POINTER(Tensor5), C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]),
-    "b200unet_conv3d_simt": (C.c_int, [C.POINTER(Tensor5), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                       C.POINTER(Tensor5), C.c_void_p]),
     "b200unet_channel_stats": (C.c_int, [C.POINTER(Tensor5), C.c_void_p, C.c_int, C.c_void_p]),
     "b200unet_gn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
@@ -108,11 +106,18 @@ _SIGS = {
     "b200unet_plan_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "b200unet_plan_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "b200unet_plan_profile_dump": (C.c_int, [C.c_void_p, C.c_char_p]),
+}
+
+# diagnostics (include/b200unet_diag.h): hardware probes + SIMT cross-check, used by tools/ only
+_DIAG_SIGS = {
+    "b200unet_conv3d_simt": (C.c_int, [C.POINTER(Tensor5), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.POINTER(Tensor5), C.c_void_p]),
     "b200unet_umma_rate": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200unet_umma_probe": (C.c_int, [C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
+DIAG_SYMBOLS = tuple(_DIAG_SIGS)
 
 
 def load_library():
@@ -123,7 +128,7 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         build_library()
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in _SIGS.items():
+    for name, (res, args) in list(_SIGS.items()) + list(_DIAG_SIGS.items()):
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args

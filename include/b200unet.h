@@ -84,10 +84,6 @@ int b200unet_conv3d(const b200unet_conv_desc* desc, void* stream);
 int b200unet_conv3d_wgrad(const b200unet_tensor* a, const b200unet_tensor* dy, int ksz, int stride, int cip, int cop,
                           float* dw, void* stream);
 
-/* ---- SIMT direct convolution on the same packed operands (cross-check only; not used by the model path) */
-int b200unet_conv3d_simt(const b200unet_tensor* x, const void* w_hi, const void* w_lo, int ksz, int stride,
-                         const b200unet_tensor* y, void* stream);
-
 /* ---- GroupNorm(G, C, eps, affine) + ReLU (myronenko.py:17-31): statistics, apply, backward */
 int b200unet_channel_stats(const b200unet_tensor* x, double* stats, int stats_ld, void* stream);
 int b200unet_gn_finalize(const double* stats, const float* gamma, const float* beta, int n, int c, int c_ld, int groups,
@@ -163,16 +159,6 @@ int b200unet_plan_profile_begin(b200unet_plan* plan, int max_launches);
 int b200unet_plan_profile_end(b200unet_plan* plan, double* ms_by_cat, int64_t* launches_by_cat, int ncat);
 /* while profiling: write one CSV row per recorded launch (index, category, milliseconds, op label) */
 int b200unet_plan_profile_dump(b200unet_plan* plan, const char* path);
-
-/* ---- tcgen05 shared-memory-descriptor probe (diagnostic; see profiles/ and DESIGN.md) */
-int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream);
-/* tcgen05.mma issue-rate micro-benchmark (M=128, N=n, K=16): cycles for reps*inner MMAs per CTA -> out[cta].
- * copy_bytes > 0: a second warp streams bulk copies of copy_bytes (<= 32768, multiple of 16) from copy_src into
- * shared memory for the whole duration (operand-write pressure); bytes copied per CTA -> out[ctas + cta].
- * commit_each_rep: stage hand-back after every `inner` MMAs: bit 0 tcgen05.commit (to an unobserved mbarrier), bit 1 an
- * mbarrier wait that succeeds immediately, bit 2 tcgen05.fence::after_thread_sync. */
-int b200unet_umma_rate(int n, int layout, int a_sbo, int b_sbo, int a_step, int inner, int reps, int ctas, int64_t* out,
-                       const void* copy_src, int copy_bytes, int commit_each_rep, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,8 +13,8 @@ from oracle import UNetConfig, unet3d_state_dict_spec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "b200unet.h")).read()
+def _declared_symbols(header="b200unet.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b200unet_[a-z0-9_]+)\s*\(", text)))
 
@@ -27,6 +27,10 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(raw, name), "missing export: " + name
     assert set(pkg.lib.EXPORTED_SYMBOLS) == set(declared)      # the binding covers the whole header
+    diag = _declared_symbols("b200unet_diag.h")                # diagnostics live in their own header
+    assert set(pkg.lib.DIAG_SYMBOLS) == set(diag) and not set(diag) & set(declared)
+    for name in diag:
+        assert hasattr(raw, name), "missing diagnostic export: " + name
     assert lib.b200unet_version() >= 100
     assert lib.b200unet_last_error() is not None
 

@@ -59,8 +59,6 @@ def test_conv3d_forward(pkg, cin, cout, dims, ksz, stride, split):
         assert float(y.hi[..., cout:].float().abs().max()) == 0.0
 
 
-@pytest.mark.skipif(os.environ.get("B200UNET_RUN_WIDE_PARITY") != "1",
-                    reason="written after the round's GPU budget was spent; enable with B200UNET_RUN_WIDE_PARITY=1 (round 2: make it default)")
 @pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("cin,cout,dims,mode", [
     (128, 128, (4, 16, 8), "plain"), (256, 192, (2, 16, 16), "plain"), (96, 160, (6, 16, 8), "plain"),
