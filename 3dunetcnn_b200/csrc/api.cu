@@ -73,6 +73,7 @@ int b200unet_conv3d(const b200unet_conv_desc* d, void* stream) {
   op.scale = d->scale; op.stats = d->stats; op.stats_ld = d->stats_ld; op.mode = d->mode;
   if (d->gn_x) { gx = to_act(d->gn_x); op.gn_x = &gx; }
   op.coef = d->coef; op.coef_ld = d->coef_ld; op.slope = d->slope; op.bstats = d->bstats;
+  op.cls_mode = d->cls_mode;
   return launch_igemm_conv(op, to_stream(stream));
 }
 
@@ -144,17 +145,47 @@ int b200unet_head_bwd(const b200unet_tensor* x, const float* w, int n_out, const
   return launch_head_bwd(to_act(x), w, n_out, dlogits, to_act(dx), dw, to_stream(stream));
 }
 
-int b200unet_dice_fwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+int b200unet_dice_fwd(const float* logits, const void* target, int n, int c, int64_t spatial, int flags,
                       float smooth_nr, float smooth_dr, double* sums, float* loss, void* stream) {
   NOT_NULL(logits); NOT_NULL(target); NOT_NULL(sums); NOT_NULL(loss);
-  return launch_dice_fwd(logits, target, n, c, spatial, flags, smooth_nr, smooth_dr, sums, loss, to_stream(stream));
+  return launch_dice_fwd(logits, reinterpret_cast<const uint8_t*>(target), n, c, spatial, flags, smooth_nr, smooth_dr, sums, loss, to_stream(stream));
 }
-int b200unet_dice_bwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+int b200unet_dice_bwd(const float* logits, const void* target, int n, int c, int64_t spatial, int flags,
                       float smooth_nr, float smooth_dr, const double* sums, const float* grad_out, float* dlogits,
                       void* stream) {
   NOT_NULL(logits); NOT_NULL(target); NOT_NULL(sums); NOT_NULL(grad_out); NOT_NULL(dlogits);
-  return launch_dice_bwd(logits, target, n, c, spatial, flags, smooth_nr, smooth_dr, sums, grad_out, dlogits,
+  return launch_dice_bwd(logits, reinterpret_cast<const uint8_t*>(target), n, c, spatial, flags, smooth_nr, smooth_dr, sums, grad_out, dlogits,
                          to_stream(stream));
+}
+
+int b200unet_tiles_gather(const float* vol, int n, int c, int d, int h, int w, const int32_t* starts, int ntiles, int rd, int rh,
+                          int rw, float* tiles, void* stream) {
+  NOT_NULL(vol); NOT_NULL(starts); NOT_NULL(tiles);
+  return launch_tiles_gather(vol, n, c, d, h, w, starts, ntiles, rd, rh, rw, tiles, to_stream(stream));
+}
+int b200unet_tiles_scatter(const float* pred, int c, const int32_t* starts, int ntiles, int rd, int rh, int rw,
+                           const float* importance, float* out, int n, int d, int h, int w, void* stream) {
+  NOT_NULL(pred); NOT_NULL(starts); NOT_NULL(importance); NOT_NULL(out);
+  return launch_tiles_scatter(pred, c, starts, ntiles, rd, rh, rw, importance, out, n, d, h, w, to_stream(stream));
+}
+int b200unet_tiles_count(const int32_t* starts_d, int nd, const int32_t* starts_h, int nh, const int32_t* starts_w, int nw, int rd,
+                         int rh, int rw, const float* importance, float* cnt, int d, int h, int w, void* stream) {
+  return launch_tiles_count(starts_d, nd, starts_h, nh, starts_w, nw, rd, rh, rw, importance, cnt, d, h, w, to_stream(stream));
+}
+int b200unet_tiles_normalize(float* out, const float* cnt, int nc, int64_t spatial, void* stream) {
+  NOT_NULL(out); NOT_NULL(cnt);
+  return launch_tiles_normalize(out, cnt, nc, spatial, to_stream(stream));
+}
+int b200unet_one_hot(const float* data, int n, int64_t spatial, const float* values, const int32_t* begin, int n_channels,
+                     int do_round, uint8_t* y, void* stream) {
+  return launch_one_hot(data, n, spatial, values, begin, n_channels, do_round, y, to_stream(stream));
+}
+int b200unet_zscore(const float* x, int groups, int64_t spatial, int nonzero, double* stats, float* y, void* stream) {
+  return launch_zscore(x, groups, spatial, nonzero, stats, y, to_stream(stream));
+}
+int b200unet_label_map(const float* p, int n_labels, int64_t spatial, const int32_t* labels, int act, float threshold,
+                       int hierarchy, int sum_then_threshold, int16_t* out, void* stream) {
+  return launch_label_map(p, n_labels, spatial, labels, act, threshold, hierarchy, sum_then_threshold, out, to_stream(stream));
 }
 
 int b200unet_umma_probe(const int32_t* tests, int ntests, float* out, void* stream) {

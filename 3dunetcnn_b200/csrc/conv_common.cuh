@@ -12,6 +12,10 @@ struct ConvMaps {
   CUtensorMap b[2][2];
   CUtensorMap o[2];     // output tile stores (hi/lo): the epilogue stages 128 x BN tiles in shared memory and TMA-stores them
 };
+// parity-class mode of the streaming kernel (stride-2 data gradient): one output map per class and hi/lo
+struct ConvClassMaps {
+  CUtensorMap oc[8][2];
+};
 
 // Row `r` / 16-byte chunk `c` of a [128 rows][CB channels] bf16 staging tile laid out the way a TMA store with the
 // matching 32B/64B/128B swizzle expects it (absolute-address XOR; the tile base is 1024-byte aligned).
@@ -40,6 +44,12 @@ struct ConvArgs {
   double* bstats;
   const float* bias;   // optional per-output-channel bias (ConvTranspose3d, decoder.py:101-102)
   int zero_last;       // force the high boundary plane/row/column of the output to exactly 0 (F.pad after ConvT, unet.py:38)
+  // parity-class mode (streaming kernel only; blockIdx.z = class (pd,ph,pw) = 4*pd + 2*ph + pw): the output tensor has
+  // twice the source extent, class c computes out[2j + p] = sum over its tap list of src[j + delta] * W[tap].
+  // cls_tap entry: bits 0-4 packed-weight tap index, bit 5 / 6 / 7 = delta_w / delta_h / delta_d (0 or +1).
+  int cls_mode;
+  unsigned char cls_n[8];
+  unsigned char cls_tap[8][8];
 };
 
 __device__ __forceinline__ void epi_load8(const bf16* hi, const bf16* lo, long long off, float* v) {

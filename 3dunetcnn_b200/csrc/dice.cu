@@ -5,7 +5,8 @@
 //   p = sigmoid(x);  per (n,c):  I = sum p*t,  P = sum p (or p^2),  T = sum t (or t^2)
 //   f = 1 - (2I + nr) / (P + T + dr)      [jaccard: denominator 2*(P + T - I)]
 //   loss = mean_{n,c} f                   [batch=True: sums are pooled over n first]
-// logits are NCDHW fp32, targets uint8 one-hot (unet3d/transforms/one_hot.py:10) - read as stored, no casts in HBM.
+// logits are NCDHW fp32, targets uint8 one-hot (unet3d/transforms/one_hot.py:10) - read as stored, no casts in HBM - or
+// fp32 (soft / interpolated / label-smoothed targets, which MONAI accepts: flag bit 6).
 #include "kernels.h"
 
 namespace b200 {
@@ -31,12 +32,13 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // grid (chunks, N*C); sums[(n*C+c)*3 + {0,1,2}] += (I, P, T)
-__global__ void k_dice_sums(const float* __restrict__ x, const uint8_t* __restrict__ t, long long S, DiceFlags f,
+template <typename TT>
+__global__ void k_dice_sums(const float* __restrict__ x, const TT* __restrict__ t, long long S, DiceFlags f,
                             double* __restrict__ sums) {
   __shared__ double sh[32];
   const long long base = (long long)blockIdx.y * S;
   float aI = 0.f, aP = 0.f, aT = 0.f;
-  if ((S & 3) == 0) {
+  if ((S & 3) == 0 && sizeof(TT) == 1) {
     const float4* x4 = reinterpret_cast<const float4*>(x + base);
     const uchar4* t4 = reinterpret_cast<const uchar4*>(t + base);
     const long long n4 = S >> 2;
@@ -103,7 +105,8 @@ __global__ void k_dice_finalize(const double* __restrict__ sums, int N, int C, D
 // dL/dx = g * w_nc * [ dF/dI * t + dF/dP * dP/dp ] * p(1-p)
 //   F = 1 - (2I+nr)/(Den+dr);  plain: Den = P+T  ->  dF/dI = -2/D', dF/dP = (2I+nr)/D'^2
 //   jaccard: Den = 2(P+T-I)    ->  dF/dI = -2/D' - 2(2I+nr)/D'^2 , dF/dP = 2(2I+nr)/D'^2          (D' = Den + dr)
-__global__ void k_dice_bwd(const float* __restrict__ x, const uint8_t* __restrict__ t, int N, int C, long long S,
+template <typename TT>
+__global__ void k_dice_bwd(const float* __restrict__ x, const TT* __restrict__ t, int N, int C, long long S,
                            DiceFlags f, float nr, float dr, const double* __restrict__ sums,
                            const float* __restrict__ grad_out, float* __restrict__ dx) {
   const int nc = blockIdx.y;
@@ -153,7 +156,8 @@ int launch_dice_fwd(const float* logits, const uint8_t* target, int N, int C, lo
   int chunks = (int)(per < 1 ? 1 : per);
   int cap = (148 * 8 + N * C - 1) / (N * C);
   if (chunks > cap) chunks = cap < 1 ? 1 : cap;
-  k_dice_sums<<<dim3(chunks, N * C), 256, 0, st>>>(logits, target, S, f, sums);
+  if (flags & 64) k_dice_sums<float><<<dim3(chunks, N * C), 256, 0, st>>>(logits, reinterpret_cast<const float*>(target), S, f, sums);
+  else k_dice_sums<uint8_t><<<dim3(chunks, N * C), 256, 0, st>>>(logits, target, S, f, sums);
   B200_CHECK_CUDA(cudaGetLastError());
   k_dice_finalize<<<1, 32, 0, st>>>(sums, N, C, f, nr, dr, loss);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -167,7 +171,10 @@ int launch_dice_bwd(const float* logits, const uint8_t* target, int N, int C, lo
   int chunks = (int)(per < 1 ? 1 : per);
   int cap = (148 * 8 + N * C - 1) / (N * C);
   if (chunks > cap) chunks = cap < 1 ? 1 : cap;
-  k_dice_bwd<<<dim3(chunks, N * C), 256, 0, st>>>(logits, target, N, C, S, f, nr, dr, sums, grad_out, dlogits);
+  if (flags & 64)
+    k_dice_bwd<float><<<dim3(chunks, N * C), 256, 0, st>>>(logits, reinterpret_cast<const float*>(target), N, C, S, f, nr, dr, sums,
+                                                            grad_out, dlogits);
+  else k_dice_bwd<uint8_t><<<dim3(chunks, N * C), 256, 0, st>>>(logits, target, N, C, S, f, nr, dr, sums, grad_out, dlogits);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -41,7 +41,8 @@ struct ConvCfg {
 };
 
 template <int BN, int KC>
-__global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ ConvMaps maps, const ConvArgs p) {
+__global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ ConvMaps maps, const ConvArgs p,
+                                                    const __grid_constant__ ConvClassMaps cmaps) {
   using Cfg = ConvCfg<BN, KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,7 +92,9 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_iters = (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
+  const int cls = p.cls_mode ? (int)blockIdx.z : 0;   // parity class (pd, ph, pw) of the outputs this CTA produces
+  const int total_iters = p.cls_mode ? (int)p.cls_n[cls] * p.kchunks[0] * p.npass
+                                     : (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
@@ -102,9 +105,17 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
         const int nt = p.ntaps[src];
         if (nt == 0) continue;
         const int ks = p.ksz[src], pad = ks >> 1, sd = p.stride[src];
-        for (int tap = 0; tap < nt; ++tap) {
-          const int kd = tap / (ks * ks), kh = (tap / ks) % ks, kw = tap % ks;
-          const int cw = w0 * sd + kw - pad, ch = h0 * sd + kh - pad, cd = d0 * sd + kd - pad;
+        const int ntap_loop = p.cls_mode ? (int)p.cls_n[cls] : nt;
+        for (int ti = 0; ti < ntap_loop; ++ti) {
+          int tap = ti, cw, ch, cd;
+          if (p.cls_mode) {   // class tap list: source voxel j + delta, packed-weight tap index
+            const int e = p.cls_tap[cls][ti];
+            tap = e & 31;
+            cw = w0 + ((e >> 5) & 1); ch = h0 + ((e >> 6) & 1); cd = d0 + ((e >> 7) & 1);
+          } else {
+            const int kd = tap / (ks * ks), kh = (tap / ks) % ks, kw = tap % ks;
+            cw = w0 * sd + kw - pad; ch = h0 * sd + kh - pad; cd = d0 * sd + kd - pad;
+          }
           for (int kc = 0; kc < p.kchunks[src]; ++kc) {
             for (int pass = 0; pass < p.npass; ++pass) {
               const int s = it % Cfg::STAGES;
@@ -151,7 +162,10 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     const int wl = row % p.tw, hl = (row / p.tw) % p.th, dl = row / (p.tw * p.th);
     const int w = w0 + wl, h = h0 + hl, d = d0 + dl;
     const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
-    const long long vox = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+    // side inputs (residual) are indexed in the OUTPUT tensor: in class mode that is voxel 2j + p of a 2x grid
+    const long long vox = p.cls_mode
+        ? (((long long)n * (2 * p.Do) + 2 * d + ((cls >> 2) & 1)) * (2 * p.Ho) + 2 * h + ((cls >> 1) & 1)) * (2 * p.Wo) + 2 * w + (cls & 1)
+        : (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
     conv_epilogue_prefetch(p, n0, BN, vox, valid);
     asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
     mbar_wait(tfull_bar, 0);
@@ -167,11 +181,13 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 64) {
       constexpr int CBO = BN < 64 ? BN : 64;
+      const CUtensorMap* mo_hi = p.cls_mode ? &cmaps.oc[cls][0] : &maps.o[0];
+      const CUtensorMap* mo_lo = p.cls_mode ? &cmaps.oc[cls][1] : &maps.o[1];
 #pragma unroll
       for (int cb = 0; cb < BN / CBO; ++cb) {
         if (n0 + cb * CBO < p.Cout) {
-          tma_store_5d(&maps.o[0], smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
-          if (split) tma_store_5d(&maps.o[1], smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+          tma_store_5d(mo_hi, smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+          if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
         }
       }
       tma_store_commit();
@@ -201,7 +217,7 @@ static void pick_tile(int Wo, int Ho, int Do, int& tw, int& th, int& td) {
 }
 
 template <int BN, int KC>
-static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cudaStream_t st) {
+static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cudaStream_t st, const ConvClassMaps& cmaps) {
   using Cfg = ConvCfg<BN, KC>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -211,7 +227,7 @@ static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cud
                                          Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  k_igemm_conv<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, args);
+  k_igemm_conv<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, args, cmaps);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -230,7 +246,7 @@ static int sm_count() {
 
 int launch_igemm_conv(const ConvOp& op, cudaStream_t st) {
   static const bool no_halo = getenv("B200UNET_NO_HALO") != nullptr;
-  if (!no_halo && (op.nsrc == 1 || op.nsrc == 2) && conv_halo_eligible(op)) return launch_conv_halo(op, sm_count(), st);
+  if (!no_halo && !op.cls_mode && (op.nsrc == 1 || op.nsrc == 2) && conv_halo_eligible(op)) return launch_conv_halo(op, sm_count(), st);
   return launch_igemm_conv_streaming(op, st);
 }
 
@@ -243,9 +259,11 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
   memset(&a, 0, sizeof(a));
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
-  a.N = out.N; a.Do = out.D; a.Ho = out.H; a.Wo = out.W; a.Cout = out.C;
-  pick_tile(out.W, out.H, out.D, a.tw, a.th, a.td);
-  a.tiles_w = ceil_div(out.W, a.tw); a.tiles_h = ceil_div(out.H, a.th); a.tiles_d = ceil_div(out.D, a.td);
+  // class mode: the GEMM rows are the voxels of ONE parity class of the output = the source grid
+  const int gD = op.cls_mode ? out.D / 2 : out.D, gH = op.cls_mode ? out.H / 2 : out.H, gW = op.cls_mode ? out.W / 2 : out.W;
+  a.N = out.N; a.Do = gD; a.Ho = gH; a.Wo = gW; a.Cout = out.C;
+  pick_tile(gW, gH, gD, a.tw, a.th, a.td);
+  a.tiles_w = ceil_div(gW, a.tw); a.tiles_h = ceil_div(gH, a.th); a.tiles_d = ceil_div(gD, a.td);
   int cin_max = 0;
   bool split = false;
   for (int s = 0; s < op.nsrc; ++s) {
@@ -255,6 +273,11 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     B200_REQUIRE(c.x.C % 8 == 0 && c.x.ld % 8 == 0, E_UNSUPPORTED, "igemm_conv: Cin=%d must be a multiple of 8", c.x.C);
     B200_REQUIRE(c.x.N == out.N, E_INVALID, "igemm_conv: batch mismatch");
     const int pad = c.ksz / 2;
+    if (op.cls_mode)
+      B200_REQUIRE(op.nsrc == 1 && c.ksz == 3 && 2 * c.x.D == out.D && 2 * c.x.H == out.H && 2 * c.x.W == out.W && op.mode == 0 &&
+                       !op.stats && !op.bias && !op.zero_last,
+                   E_INVALID, "igemm_conv: class mode needs one 3x3x3 source at half the output extent and a plain epilogue");
+    else
     B200_REQUIRE((c.x.D + 2 * pad - c.ksz) / c.stride + 1 == out.D && (c.x.H + 2 * pad - c.ksz) / c.stride + 1 == out.H &&
                      (c.x.W + 2 * pad - c.ksz) / c.stride + 1 == out.W,
                  E_INVALID, "igemm_conv: source %d dims %dx%dx%d (k%d s%d) do not produce output %dx%dx%d", s, c.x.D,
@@ -273,12 +296,13 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     const ConvSrc& c = op.src[s];
     a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = c.stride;
     a.kchunks[s] = ceil_div(c.x.C, KC);
+    const int estride = op.cls_mode ? 1 : c.stride;
     B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
-                          c.stride, swz, c.x.vD, c.x.vH, c.x.vW));
+                          estride, swz, c.x.vD, c.x.vH, c.x.vW));
     B200_TRY(make_w_map(&maps.b[s][0], c.w_hi, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     if (split) {
       B200_TRY(make_act_map(&maps.a[s][1], c.x.lo, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
-                            c.stride, swz, c.x.vD, c.x.vH, c.x.vW));
+                            estride, swz, c.x.vD, c.x.vH, c.x.vW));
       B200_TRY(make_w_map(&maps.b[s][1], c.w_lo, a.ntaps[s], op.Cop, c.Cip, KC, BN, swz));
     }
   }
@@ -286,7 +310,33 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
   a.mode = op.mode;
   a.out_hi = out.hi; a.out_lo = out.lo; a.ldo = out.ld;
   if (split) B200_REQUIRE(out.lo != nullptr, E_INVALID, "igemm_conv: split mode needs a lo output");
-  {
+  ConvClassMaps cmaps;
+  memset(&cmaps, 0, sizeof(cmaps));
+  if (op.cls_mode) {
+    // data gradient of y[o] = sum_k x[2o + k - 1] w[k]: dx[2j] = dy[j] w[1]; dx[2j+1] = dy[j] w[2] + dy[j+1] w[0].  With the
+    // flipped pack Wd[k'] = w[2 - k'] (what emit_dgrad binds): even outputs use k' = 1 (delta 0), odd outputs k' = 0
+    // (delta 0) and k' = 2 (delta +1); dy[j+1] beyond the grid reads as zero (TMA out-of-bounds fill).
+    a.cls_mode = 1;
+    const int cbo = BN < 64 ? BN : 64;
+    for (int cls = 0; cls < 8; ++cls) {
+      const int pd = (cls >> 2) & 1, ph = (cls >> 1) & 1, pw = cls & 1;
+      int n = 0;
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = (pd ? kd != 1 : kd == 1) && (ph ? kh != 1 : kh == 1) && (pw ? kw != 1 : kw == 1);
+            if (!ok) continue;
+            a.cls_tap[cls][n++] = (unsigned char)((kd * 9 + kh * 3 + kw) | ((kw == 2) << 5) | ((kh == 2) << 6) | ((kd == 2) << 7));
+          }
+      a.cls_n[cls] = (unsigned char)n;
+      B200_TRY(make_act_map_class(&cmaps.oc[cls][0], out.hi, out.N, out.D, out.H, out.W, out.C, out.ld, pd, ph, pw, cbo, a.tw, a.th,
+                                  a.td, swz_for_bytes(cbo * 2)));
+      if (split)
+        B200_TRY(make_act_map_class(&cmaps.oc[cls][1], out.lo, out.N, out.D, out.H, out.W, out.C, out.ld, pd, ph, pw, cbo, a.tw,
+                                    a.th, a.td, swz_for_bytes(cbo * 2)));
+    }
+    maps.o[0] = cmaps.oc[0][0];   // keeps the (unused) plain output descriptor valid
+  } else {
     const int cbo = BN < 64 ? BN : 64;
     B200_TRY(make_act_map(&maps.o[0], out.hi, out.N, out.D, out.H, out.W, out.C, out.ld, cbo, a.tw, a.th, a.td, 1,
                           swz_for_bytes(cbo * 2)));
@@ -308,9 +358,9 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     a.coef = reinterpret_cast<const float4*>(op.coef); a.coef_ld = op.coef_ld;
     a.slope = op.slope; a.bstats = op.bstats;
   }
-  dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN));
+  dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN), op.cls_mode ? 8u : 1u);
 #define B200_CONV_CASE(bn, kc) \
-  if (BN == bn && KC == kc) return launch_cfg<bn, kc>(maps, a, grid, st);
+  if (BN == bn && KC == kc) return launch_cfg<bn, kc>(maps, a, grid, st, cmaps);
   B200_CONV_CASE(16, 16) B200_CONV_CASE(16, 32) B200_CONV_CASE(16, 64)
   B200_CONV_CASE(32, 16) B200_CONV_CASE(32, 32) B200_CONV_CASE(32, 64)
   B200_CONV_CASE(64, 16) B200_CONV_CASE(64, 32) B200_CONV_CASE(64, 64)

@@ -49,12 +49,30 @@ int launch_conv_simt(const Act& x, const bf16* whi, const bf16* wlo, int ksz, in
                      cudaStream_t st);
 
 // ---- Dice criterion (dice.cu)
-// flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum
+// flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum,
+// bit6 target is fp32 (soft labels) instead of uint8
 int launch_dice_fwd(const float* logits, const uint8_t* target, int N, int C, long long S, int flags,
                     float smooth_nr, float smooth_dr, double* sums, float* loss, cudaStream_t st);
 int launch_dice_bwd(const float* logits, const uint8_t* target, int N, int C, long long S, int flags,
                     float smooth_nr, float smooth_dr, const double* sums, const float* grad_out, float* dlogits,
                     cudaStream_t st);
+
+// ---- steps before / after the path (prepost.cu): sliding-window tiles, one-hot targets, z-score, label maps
+#define B200_MAX_TILES 16
+#define B200_MAX_LABEL_CHANNELS 16
+#define B200_MAX_LABEL_VALUES 64
+int launch_tiles_gather(const float* vol, int N, int C, int D, int H, int W, const int32_t* starts, int ntiles, int rd, int rh,
+                        int rw, float* tiles, cudaStream_t st);
+int launch_tiles_scatter(const float* pred, int C, const int32_t* starts, int ntiles, int rd, int rh, int rw, const float* imp,
+                         float* out, int N, int D, int H, int W, cudaStream_t st);
+int launch_tiles_count(const int32_t* sd_dev, int nd, const int32_t* sh_dev, int nh, const int32_t* sw_dev, int nw, int rd, int rh,
+                       int rw, const float* imp, float* cnt, int D, int H, int W, cudaStream_t st);
+int launch_tiles_normalize(float* out, const float* cnt, int NC, long long S, cudaStream_t st);
+int launch_one_hot(const float* data, int N, long long S, const float* values, const int32_t* begin, int n_channels, int do_round,
+                   uint8_t* y, cudaStream_t st);
+int launch_zscore(const float* x, int groups, long long S, int nonzero, double* stats, float* y, cudaStream_t st);
+int launch_label_map(const float* p, int L, long long S, const int32_t* labels, int act, float thr, int hierarchy,
+                     int sum_then_threshold, int16_t* out, cudaStream_t st);
 
 // ---- tensor-core implicit-GEMM convolution (igemm_conv.cu)
 struct ConvSrc {
@@ -83,6 +101,9 @@ struct ConvOp {
   double* bstats;      // mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat)
   const float* bias;   // mode 0: optional per-channel bias
   int zero_last;       // mode 0: output voxels on the high boundary of each axis are forced to 0
+  int cls_mode;        // 1: data gradient of a 3x3x3 stride-2 padding-1 convolution WITHOUT zero insertion: src[0].x = dY (low
+                       // resolution), src[0].w = the flipped data-gradient pack, out = dX at twice the extent; eight
+                       // parity-class implicit GEMMs (27 tap products in total instead of 8 x 27) in one launch
 };
 
 int launch_igemm_conv(const ConvOp& op, cudaStream_t st);   // dispatcher: halo-resident kernel when eligible

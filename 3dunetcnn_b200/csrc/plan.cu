@@ -12,6 +12,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "../../include/b200unet.h"
@@ -132,8 +133,8 @@ struct b200unet_plan {
   double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
   bool have_drop = false;
-  std::vector<size_t> stats_allocs;  // deferred: sizes
-  std::vector<size_t> bz_allocs;
+  bool infer = false;       // forward-only plan: no backward schedule / buffers, forward temporaries are recycled
+  std::vector<std::pair<size_t, std::pair<size_t, size_t>>> free_bufs;   // (bytes, (off_hi, off_lo)) of released buffers
 
   size_t alloc(size_t bytes) {
     size_t off = (cur + 1023) & ~size_t(1023);
@@ -229,17 +230,41 @@ static void build_param_spec(Plan& P) {
 static int new_buf(Plan& P, int N, int D, int H, int W, int C) {
   Buf b;
   size_t bytes = (size_t)N * D * H * W * C * sizeof(bf16);
-  b.off_hi = P.alloc(bytes);
-  b.off_lo = P.split ? P.alloc(bytes) : 0;
+  bool reused = false;
+  for (size_t i = 0; i < P.free_bufs.size(); ++i)
+    if (P.free_bufs[i].first == bytes) {   // forward-only plans: take a released buffer of the same size
+      b.off_hi = P.free_bufs[i].second.first;
+      b.off_lo = P.free_bufs[i].second.second;
+      P.free_bufs.erase(P.free_bufs.begin() + i);
+      reused = true;
+      break;
+    }
+  if (!reused) {
+    b.off_hi = P.alloc(bytes);
+    b.off_lo = P.split ? P.alloc(bytes) : 0;
+  }
   b.N = N; b.D = D; b.H = H; b.W = W; b.C = C;
   b.stats_off = -1;
   P.bufs.push_back(b);
   return (int)P.bufs.size() - 1;
 }
 
+// forward-only plans: the launches are stream-ordered, so a buffer whose last reader has been emitted can back a later
+// tensor.  Only whole buffers are released (never a channel slice of a concat buffer while the other half is live).
+static void release_buf(Plan& P, int buf) {
+  if (!P.infer || buf < 0) return;
+  const Buf& b = P.bufs[buf];
+  P.free_bufs.push_back({(size_t)b.N * b.D * b.H * b.W * b.C * sizeof(bf16), {b.off_hi, b.off_lo}});
+}
+
+static void release_if_whole(Plan& P, TRef t);
+
 static TRef full(const Plan& P, int buf) { TRef t = {buf, 0, P.bufs[buf].C, 0}; return t; }
 static TRef slice(TRef t, int c0, int c) { TRef r = {t.buf, t.c0 + c0, c, t.vis_m1}; return r; }
 static TRef masked(TRef t) { TRef r = t; r.vis_m1 = 1; return r; }
+static void release_if_whole(Plan& P, TRef t) {
+  if (t.valid() && t.c0 == 0 && t.c == P.bufs[t.buf].C) release_buf(P, t.buf);
+}
 
 static Act act_of(const Plan& P, const RunCtx& cx, TRef t) {
   const Buf& b = P.bufs[t.buf];
@@ -281,6 +306,7 @@ static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, in
   c.name = key;
   c.Co = Co; c.Ci = Ci; c.Cop = round_up(Co, 8); c.Cip = round_up(Ci, 8);
   c.ksz = ksz; c.stride = stride; c.T = ksz * ksz * ksz;
+  need_dgrad = need_dgrad && !P.infer;
   c.need_dgrad = need_dgrad;
   c.transposed = false;
   c.pb = -1;
@@ -290,7 +316,7 @@ static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, in
   c.wd_hi = need_dgrad ? P.alloc(n * 2) : 0;
   c.wd_lo = (need_dgrad && P.split) ? P.alloc(n * 2) : 0;
   c.dw = P.bz_bytes;  // relative to bz_off
-  P.bz_bytes += (n * sizeof(float) + 255) & ~size_t(255);
+  if (!P.infer) P.bz_bytes += (n * sizeof(float) + 255) & ~size_t(255);
   P.convs.push_back(c);
   return (int)P.convs.size() - 1;
 }
@@ -302,9 +328,9 @@ static int new_norm(Plan& P, const std::string& prefix, int C, int Cld, long lon
   n.pb = P.find_param(prefix + ".bias");
   n.C = C; n.Cld = Cld; n.G = groups_for(C, P.d.norm_groups); n.S = S;
   n.coef = P.alloc((size_t)P.d.batch * Cld * 4 * sizeof(float));
-  n.coef2 = P.alloc((size_t)P.d.batch * Cld * 2 * sizeof(float));
+  n.coef2 = P.infer ? 0 : P.alloc((size_t)P.d.batch * Cld * 2 * sizeof(float));
   n.bstats = P.bz_bytes;
-  P.bz_bytes += ((size_t)P.d.batch * Cld * 2 * sizeof(double) + 255) & ~size_t(255);
+  if (!P.infer) P.bz_bytes += ((size_t)P.d.batch * Cld * 2 * sizeof(double) + 255) & ~size_t(255);
   P.norms.push_back(n);
   return (int)P.norms.size() - 1;
 }
@@ -400,15 +426,17 @@ static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
 
 // data gradient through conv `ci` (stride 1):  out = conv(dy, Wd)  with either the GN/ReLU backward epilogue
 // (ni >= 0, gn_x = raw input of the norm) or a plain epilogue (+res, *dropout scale).
-static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale, double alg_macs) {
-  const int cat = goes_halo(P, dy, P.convs[ci].ksz, P.convs[ci].transposed ? 2 : 1, false, out) ? CAT_CONV_HALO : CAT_CONV_DGRAD;
+static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TRef res, bool scale, double alg_macs,
+                       bool cls_mode = false) {
+  const int cat = (!cls_mode && goes_halo(P, dy, P.convs[ci].ksz, P.convs[ci].transposed ? 2 : 1, false, out)) ? CAT_CONV_HALO : CAT_CONV_DGRAD;
   P.macs[cat] += alg_macs;
   push_op(P.bwd, std::string(ni >= 0 ? "dgrad+gnrelu " : "dgrad ") + P.convs[ci].name + " " + shape_of(P, dy) + "->" + shape_of(P, out),
-          [&P, ci, dy, out, ni, gn_x, res, scale, cat](RunCtx& cx) -> int {
+          [&P, ci, dy, out, ni, gn_x, res, scale, cat, cls_mode](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     ConvOp op;
     memset(&op, 0, sizeof(op));
     op.nsrc = 1;
+    op.cls_mode = cls_mode ? 1 : 0;
     op.src[0].x = act_of(P, cx, dy);
     op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wd_hi);
     op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr;
@@ -460,7 +488,7 @@ static void emit_gn_bwd(Plan& P, int ni, TRef dz, TRef x, TRef add1, TRef dx, bo
 
 // ------------------------------------------------------------------------------------------------ residual block
 static BlockRec build_block_fwd(Plan& P, const std::string& pre, TRef X, int cin_real, int C, TRef dest, bool want_stats,
-                                bool first, bool scale_out, bool scale_in) {
+                                bool first, bool scale_out, bool scale_in, bool x_dead) {
   const Buf& xb = P.bufs[X.buf];
   const int N = xb.N, D = xb.D, H = xb.H, W = xb.W;
   const long long S = (long long)D * H * W;
@@ -480,6 +508,10 @@ static BlockRec build_block_fwd(Plan& P, const std::string& pre, TRef X, int cin
   emit_norm_fwd(P, r.n2, r.y1, r.a2);
   if (r.cs >= 0) emit_conv_fwd(P, r.c2, r.a2, r.cs, X, kNone, dest, want_stats, scale_out);
   else emit_conv_fwd(P, r.c2, r.a2, -1, kNone, X, dest, want_stats, scale_out);
+  release_buf(P, r.a1.buf);
+  release_buf(P, r.y1.buf);
+  release_buf(P, r.a2.buf);
+  if (x_dead) release_if_whole(P, X);
   return r;
 }
 
@@ -580,7 +612,7 @@ static int build(Plan& P) {
       const bool first = (li == 0 && b == 0);
       enc[li].push_back(build_block_fwd(P, "encoder.layers." + std::to_string(li) + ".blocks." + std::to_string(b), X,
                                         cin_real, C, dest, want_stats, first, /*scale_out=*/first,
-                                        /*scale_in=*/(li == 0 && b == 1)));
+                                        /*scale_in=*/(li == 0 && b == 1), /*x_dead=*/true));
       X = dest;
       cin_real = C;
     }
@@ -602,7 +634,7 @@ static int build(Plan& P) {
     for (int b = 0; b < d.decoder_blocks[i]; ++b) {
       TRef dest = full(P, new_buf(P, N, xb.D, xb.H, xb.W, in_w));
       dec[i].push_back(build_block_fwd(P, "decoder.layers." + std::to_string(i) + ".blocks." + std::to_string(b), X, in_w,
-                                       in_w, dest, /*want_stats=*/b + 1 < d.decoder_blocks[i], false, false, false));
+                                       in_w, dest, /*want_stats=*/b + 1 < d.decoder_blocks[i], false, false, false, true));
       X = dest;
     }
     const int j = L - 2 - i;
@@ -616,12 +648,14 @@ static int build(Plan& P) {
       s.cpre = new_conv(P, "decoder.pre_upsampling_blocks." + std::to_string(i) + ".weight", out_w, in_w, 1, 1, true);
       s.P = full(P, new_buf(P, N, xb.D, xb.H, xb.W, out_w));
       emit_conv_fwd(P, s.cpre, X, -1, kNone, kNone, s.P, false, false);
+      release_if_whole(P, X);
       TRef Pin = s.P, U = s.U;
       push_op(P.fwd, "upsample2x_fwd " + shape_of(P, Pin), [&P, Pin, U](RunCtx& cx) -> int {
         LAUNCHED(cx, CAT_RESAMPLE, launch_upsample2x_fwd(act_of(P, cx, Pin), act_of(P, cx, U), stats_ptr(P, cx, U), P.bufs[U.buf].C,
                                            cx.st));
         return OK;
       });
+      release_buf(P, s.P.buf);
     } else {
       // ConvTranspose3d(k3, s2, p1) + bias, then F.pad(+1 high side) = zero-insert + 3x3x3 conv with the flipped
       // kernel over a 2n grid whose last plane/row/column is forced to 0 (decoder.py:101-102, unet.py:34-40)
@@ -636,7 +670,9 @@ static int build(Plan& P) {
         LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, Xi), act_of(P, cx, Z), 0, 0, 0, cx.st));
         return OK;
       });
+      release_if_whole(P, X);
       emit_conv_fwd(P, s.cup, s.Z, -1, kNone, kNone, s.U, true, false);
+      release_buf(P, s.Z.buf);
     }
     stages.push_back(s);
     X = s.cat;
@@ -648,7 +684,7 @@ static int build(Plan& P) {
     for (int b = 0; b < d.decoder_blocks[L - 1]; ++b) {
       TRef dest = full(P, new_buf(P, N, xb.D, xb.H, xb.W, d.base_width));
       dec[L - 1].push_back(build_block_fwd(P, "decoder.layers." + std::to_string(L - 1) + ".blocks." + std::to_string(b), X,
-                                           cin, d.base_width, dest, b + 1 < d.decoder_blocks[L - 1], false, false, false));
+                                           cin, d.base_width, dest, b + 1 < d.decoder_blocks[L - 1], false, false, false, true));
       X = dest;
       cin = d.base_width;
     }
@@ -661,7 +697,8 @@ static int build(Plan& P) {
     return OK;
   });
 
-  // ---------------- backward
+  // ---------------- backward (training plans only)
+  if (!P.infer) {
   B200_REQUIRE(d.activation == 0, E_UNSUPPORTED,
                "plan: activation inside the model (sigmoid/softmax) is inference-only; train on logits");
   push_op(P.bwd, "memset", [&P](RunCtx& cx) -> int {
@@ -717,16 +754,23 @@ static int build(Plan& P) {
     if (li > 0) {
       const int lj = li - 1;
       emit_wgrad(P, down[lj], skip[lj], g);
-      TRef Z = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
       TRef gin = g;
-      push_op(P.bwd, "zero_insert " + shape_of(P, Z), [&P, gin, Z](RunCtx& cx) -> int {
-        LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
-        return OK;
-      });
       TRef gS = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
       // dropout scale belongs to the output of encoder block (0,0): that is this tensor iff level 0 has one block
       const bool sc = (lj == 0 && d.encoder_blocks[0] == 1);
-      emit_dgrad(P, down[lj], Z, gS, -1, kNone, dskip_dec[lj], sc, conv_macs(P, down[lj], gin));
+      static const bool zero_insert = getenv("B200UNET_S2_ZERO_INSERT") != nullptr;   // A/B switch: the round-1 formulation
+      if (zero_insert) {
+        TRef Z = full(P, new_buf(P, N, Ds[lj], Hs[lj], Ws[lj], widths[lj]));
+        push_op(P.bwd, "zero_insert " + shape_of(P, Z), [&P, gin, Z](RunCtx& cx) -> int {
+          LAUNCHED(cx, CAT_RESAMPLE, launch_zero_insert(act_of(P, cx, gin), act_of(P, cx, Z), 0, 0, 0, cx.st));
+          return OK;
+        });
+        emit_dgrad(P, down[lj], Z, gS, -1, kNone, dskip_dec[lj], sc, conv_macs(P, down[lj], gin));
+      } else {
+        // eight parity-class implicit GEMMs over the un-inserted gradient (27 tap products instead of 8 x 27), TMA-stored
+        // into their interleaved positions
+        emit_dgrad(P, down[lj], gin, gS, -1, kNone, dskip_dec[lj], sc, conv_macs(P, down[lj], gin), /*cls_mode=*/true);
+      }
       g = gS;
     }
   }
@@ -739,6 +783,7 @@ static int build(Plan& P) {
     LAUNCHED(cx, CAT_PACK, launch_unpack_all(tbl, jobs, (int)P.unpack_jobs.size(), cx.ws, cx.st));
     return OK;
   });
+  }  // !P.infer
   // arenas that are bulk-zeroed
   B200_REQUIRE(P.params.size() <= 256, E_UNSUPPORTED, "plan: more than 256 parameter tensors");
   P.drop_off = P.alloc(sizeof(float) * N * d.base_width);
@@ -755,6 +800,7 @@ static int build(Plan& P) {
       j.mode = c.transposed ? 3 : 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo;
       P.pack_jobs.push_back(j);
     }
+    if (P.infer) continue;
     PackJob u = j;
     u.mode = c.transposed ? 2 : 0; u.off_hi = (long long)(P.bz_off + c.dw); u.off_lo = 0;
     P.unpack_jobs.push_back(u);
@@ -772,6 +818,7 @@ int b200unet_plan_create(const b200unet_net_desc* desc, b200unet_plan** out) {
   b200unet_plan* P = new b200unet_plan();
   P->d = *desc;
   P->split = desc->split_precision != 0;
+  P->infer = desc->inference_only != 0;
   if (P->d.norm_groups <= 0) P->d.norm_groups = 8;
   if (P->d.feature_dilation <= 0) P->d.feature_dilation = 2;
   int s = build(*P);
@@ -796,7 +843,10 @@ size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan) { return plan ? 
 
 int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
                           int save_for_backward, void* workspace, float* logits, void* stream) {
-  (void)save_for_backward;
+  if (save_for_backward && plan && plan->infer) {
+    set_error("plan_forward: save_for_backward=1 on a plan created with inference_only=1");
+    return E_INVALID;
+  }
   if (!plan || !x || !params || !workspace || !logits) { set_error("plan_forward: null argument"); return E_INVALID; }
   RunCtx cx;
   memset(&cx, 0, sizeof(cx));
@@ -819,6 +869,7 @@ int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* cons
 int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const float* const* params, float* const* grads,
                            void* workspace, void* stream) {
   if (!plan || !dlogits || !params || !grads || !workspace) { set_error("plan_backward: null argument"); return E_INVALID; }
+  if (plan->infer) { set_error("plan_backward: this plan was created with inference_only=1 (no backward schedule)"); return E_INVALID; }
   RunCtx cx;
   memset(&cx, 0, sizeof(cx));
   cx.ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));

@@ -14,6 +14,12 @@ enum Swz { SWZ_NONE = 0, SWZ_32 = 1, SWZ_64 = 2, SWZ_128 = 3 };
 int make_act_map(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int boxC, int boxW,
                  int boxH, int boxD, int estride, Swz swz, int vD = 0, int vH = 0, int vW = 0);
 
+// 5-D map over ONE PARITY CLASS (pd, ph, pw) of an NDHWC view with even extents: logical dims (C, W/2, H/2, D/2, N), element
+// (c, w, h, d, n) = tensor[n][2d+pd][2h+ph][2w+pw][c].  Used to TMA-store the output tiles of the stride-2 data gradient
+// (one implicit GEMM per output parity class) straight into their interleaved positions.
+int make_act_map_class(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int pd, int ph, int pw,
+                       int boxC, int boxW, int boxH, int boxD, Swz swz);
+
 // 3-D map over packed weights [T][R][K] bf16 (K contiguous): dims (K, R, T); box (boxK, boxR, 1).
 int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz, int boxT = 1);
 int make_w_map_kd(CUtensorMap* out, const bf16* ptr, int R, int K, int boxK, int boxR, Swz swz);

@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32 * 2), ("cip", C.c_int32 * 2), ("nsrc", C.c_int32), ("cop", C.c_int32),
                 ("out", Tensor5), ("res", C.POINTER(Tensor5)), ("scale", C.c_void_p), ("stats", C.c_void_p),
                 ("stats_ld", C.c_int32), ("mode", C.c_int32), ("gn_x", C.POINTER(Tensor5)), ("coef", C.c_void_p),
-                ("coef_ld", C.c_int32), ("slope", C.c_float), ("bstats", C.c_void_p)]
+                ("coef_ld", C.c_int32), ("slope", C.c_float), ("bstats", C.c_void_p), ("cls_mode", C.c_int32)]
 
 
 class NetDesc(C.Structure):
@@ -39,7 +39,7 @@ class NetDesc(C.Structure):
                 ("feature_dilation", C.c_int32), ("norm_groups", C.c_int32),
                 ("use_transposed_convolutions", C.c_int32), ("activation", C.c_int32),
                 ("split_precision", C.c_int32), ("batch", C.c_int32), ("depth", C.c_int32), ("height", C.c_int32),
-                ("width", C.c_int32)]
+                ("width", C.c_int32), ("inference_only", C.c_int32)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -92,6 +92,18 @@ _SIGS = {
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200unet_dice_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200unet_tiles_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "b200unet_tiles_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200unet_tiles_count": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200unet_tiles_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "b200unet_one_hot": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
+    "b200unet_zscore": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200unet_label_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.c_int, C.c_float, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
     "b200unet_plan_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(C.c_void_p)]),
     "b200unet_plan_destroy": (None, [C.c_void_p]),
     "b200unet_plan_num_params": (C.c_int, [C.c_void_p]),
@@ -223,7 +235,7 @@ def conv3d(x: Act, w_hi, w_lo, ksz: int, stride: int, out: Act, cop: int, cip: i
            w2_hi=None, w2_lo=None, cip2: int = 0, res: Optional[Act] = None, scale: Optional[torch.Tensor] = None,
            stats: Optional[torch.Tensor] = None, stats_ld: int = 0, mode: int = 0, gn_x: Optional[Act] = None,
            coef: Optional[torch.Tensor] = None, coef_ld: int = 0, slope: float = 0.0,
-           bstats: Optional[torch.Tensor] = None) -> None:
+           bstats: Optional[torch.Tensor] = None, cls_mode: int = 0) -> None:
     d = ConvDesc()
     d.x[0] = x.ct()
     d.w_hi[0] = w_hi.data_ptr()
@@ -253,6 +265,7 @@ def conv3d(x: Act, w_hi, w_lo, ksz: int, stride: int, out: Act, cop: int, cip: i
     d.coef_ld = coef_ld
     d.slope = slope
     d.bstats = bstats.data_ptr() if bstats is not None else None
+    d.cls_mode = cls_mode
     check(load_library().b200unet_conv3d(C.byref(d), stream_ptr()), "conv3d")
 
 
@@ -325,11 +338,11 @@ def head_bwd(x: Act, w, n_out, dlogits, dx: Act, dw) -> None:
 
 
 def dice_flags(sigmoid=True, squared_pred=False, jaccard=False, batch=False, include_background=True,
-               reduction="mean") -> int:
+               reduction="mean", float_target=False) -> int:
     if reduction not in ("mean", "sum"):
         raise ValueError("fused Dice supports reduction 'mean' or 'sum', got %r" % (reduction,))
     return (int(bool(sigmoid)) | (int(bool(squared_pred)) << 1) | (int(bool(jaccard)) << 2) | (int(bool(batch)) << 3)
-            | (int(not include_background) << 4) | (int(reduction == "sum") << 5))
+            | (int(not include_background) << 4) | (int(reduction == "sum") << 5) | (int(bool(float_target)) << 6))
 
 
 def dice_fwd(logits, target, flags, nr, dr, sums, loss) -> None:

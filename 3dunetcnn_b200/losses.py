@@ -32,7 +32,8 @@ class _DiceFunction(torch.autograd.Function):
         flags, nr, dr = ctx.cfg
         dlogits = torch.empty_like(logits)
         g = grad_out.detach().float().contiguous()
-        _lib.dice_bwd(logits, target, flags, nr, dr, sums, g, dlogits)
+        with torch.cuda.device(logits.device):
+            _lib.dice_bwd(logits, target, flags, nr, dr, sums, g, dlogits)
         return dlogits, None, None, None, None
 
 
@@ -59,6 +60,13 @@ class DiceLoss(nn.Module):
         out = output.as_subclass(torch.Tensor) if type(output) is not torch.Tensor else output
         tgt = target.as_subclass(torch.Tensor) if type(target) is not torch.Tensor else target
         out = out.contiguous().float()
-        if tgt.dtype != torch.uint8:
+        flags = self.flags
+        if tgt.dtype == torch.bool:
             tgt = tgt.to(torch.uint8)
-        return _DiceFunction.apply(out, tgt.contiguous(), self.flags, self.smooth_nr, self.smooth_dr)
+        elif tgt.dtype != torch.uint8:
+            # MONAI casts the target to float: soft / interpolated / label-smoothed targets are legal, so any non-uint8
+            # target takes the kernels' fp32-target path instead of being truncated to 0/1
+            tgt = tgt.float()
+            flags |= 64
+        with torch.cuda.device(out.device):
+            return _DiceFunction.apply(out, tgt.contiguous(), flags, self.smooth_nr, self.smooth_dr)

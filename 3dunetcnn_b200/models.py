@@ -50,6 +50,8 @@ class _Plan:
         self.ws_bytes = int(self.lib.b200unet_plan_workspace_bytes(self.handle))
         self.device = device
         self.workspace = None
+        self.inference_only = bool(desc.inference_only)
+        self.serial = 0          # forward passes issued with save_for_backward (see _UNetFunction.backward)
 
     def ensure_workspace(self):
         if self.workspace is None:
@@ -108,17 +110,21 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, drop, *params):
-        plan = model._plan_for(x)
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        plan = model._plan_for(x, inference_only=not need_bwd)
         n, _, d, h, w = x.shape
         logits = torch.empty((n, model.n_outputs, d, h, w), dtype=torch.float32, device=x.device)
-        ws = plan.ensure_workspace()
-        pa = _ptr_array(params)
-        need_bwd = any(p.requires_grad for p in params)
-        _lib.check(plan.lib.b200unet_plan_forward(plan.handle, x.data_ptr(), pa, drop.data_ptr() if drop is not None else None,
-                                                  int(need_bwd), ws.data_ptr(), logits.data_ptr(), _lib.stream_ptr()),
-                   "plan_forward")
+        with torch.cuda.device(x.device):   # the library launches on the current device's current stream
+            ws = plan.ensure_workspace()
+            pa = _ptr_array(params)
+            _lib.check(plan.lib.b200unet_plan_forward(plan.handle, x.data_ptr(), pa, drop.data_ptr() if drop is not None else None,
+                                                      int(need_bwd), ws.data_ptr(), logits.data_ptr(), _lib.stream_ptr()),
+                       "plan_forward")
         model.launches_last_forward = plan.last_launches()
+        if need_bwd:
+            plan.serial += 1
         ctx.plan = plan
+        ctx.serial = plan.serial
         ctx.model = model
         ctx.save_for_backward(*params)
         return logits
@@ -126,12 +132,24 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         plan = ctx.plan
+        if plan.inference_only:
+            raise RuntimeError("B200 UNet3D: backward through a forward that ran without gradients enabled")
+        if ctx.serial != plan.serial:
+            # the saved activations, GroupNorm statistics and the dropout mask live in ONE per-shape workspace: a later
+            # forward of the same shape has overwritten what this backward needs
+            raise RuntimeError("B200 UNet3D: backward of forward pass #%d, but forward pass #%d of the same input shape has "
+                               "overwritten the saved activations since; run backward before the next same-shape forward "
+                               "(one outstanding forward per input shape)" % (ctx.serial, plan.serial))
         params = ctx.saved_tensors
+        model = ctx.model
         dlogits = dlogits.contiguous().float()
-        grads = [torch.empty_like(p) for p in params]
-        _lib.check(plan.lib.b200unet_plan_backward(plan.handle, dlogits.data_ptr(), _ptr_array(params), _ptr_array(grads),
-                                                   plan.workspace.data_ptr(), _lib.stream_ptr()), "plan_backward")
-        ctx.model.launches_last_backward = plan.last_launches()
+        with torch.cuda.device(dlogits.device):
+            grads, direct = model._grad_targets(params)
+            _lib.check(plan.lib.b200unet_plan_backward(plan.handle, dlogits.data_ptr(), _ptr_array(params), _ptr_array(grads),
+                                                       plan.workspace.data_ptr(), _lib.stream_ptr()), "plan_backward")
+        model.launches_last_backward = plan.last_launches()
+        if direct:                      # flat-bucket mode: the gradients already sit in the parameters' .grad views
+            return (None, None, None) + (None,) * len(params)
         return (None, None, None) + tuple(grads)
 
 
@@ -185,6 +203,9 @@ class UNet3D(nn.Module):
         self.launches_last_forward = 0
         self.launches_last_backward = 0
         self._forced_dropout_scale: Optional[torch.Tensor] = None
+        self._flat_grads = False
+        self._grad_bucket: Optional[torch.Tensor] = None
+        self._grad_views = None
 
         # parameters under the reference's keys, default torch init
         self._keys = []
@@ -275,18 +296,64 @@ class UNet3D(nn.Module):
         nd.batch, nd.depth, nd.height, nd.width = n, d, h, w
         return nd
 
-    def _plan_for(self, x: torch.Tensor) -> _Plan:
+    def _plan_for(self, x: torch.Tensor, inference_only: bool = False) -> _Plan:
         n, _, d, h, w = x.shape
-        key = (n, d, h, w, self.precision, x.device.index)
+        key = (n, d, h, w, self.precision, x.device.index, bool(inference_only))
         plan = self._plans.get(key)
         if plan is None:
-            plan = _Plan(self._net_desc(n, d, h, w), x.device)
+            desc = self._net_desc(n, d, h, w)
+            desc.inference_only = int(bool(inference_only))
+            plan = _Plan(desc, x.device)
             spec = plan.param_spec()
             mine = [(k, tuple(p.shape)) for k, p in zip(self._keys, self.ordered_parameters())]
             if spec != mine:
                 raise RuntimeError("libb200unet parameter spec does not match the module's state_dict")
             self._plans[key] = plan
         return plan
+
+    # ------------------------------------------------------------------ gradient placement
+    def use_flat_gradients(self, enabled: bool = True) -> None:
+        """Write the parameter gradients straight into views of ONE persistent flat fp32 bucket (state-dict order) and
+        bind them as ``p.grad``: no per-step allocation, and the data-parallel exchange (``parallel.GradAllReduce``)
+        all-reduces the bucket in place without copies.  Backward then returns no gradients to autograd for the
+        parameters (hooks on them do not fire)."""
+        self._flat_grads = bool(enabled)
+        if not enabled:
+            self._grad_bucket = self._grad_views = None
+
+    def flat_gradient_bucket(self) -> Optional[torch.Tensor]:
+        return self._grad_bucket
+
+    def _bucket_views(self, params):
+        if (self._grad_bucket is None or self._grad_bucket.device != params[0].device
+                or self._grad_bucket.numel() != sum(p.numel() for p in params)):
+            self._grad_bucket = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+            views, off = [], 0
+            for p in params:
+                views.append(self._grad_bucket[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._grad_views = views
+        return self._grad_views
+
+    def _grad_targets(self, params):
+        """(tensors the library writes the gradients into, whether they are already bound as ``.grad``)."""
+        if not self._flat_grads:
+            return [torch.empty_like(p) for p in params], False
+        views = self._bucket_views(params)
+        live = self.ordered_parameters()
+        if all(p.grad is None for p in live):                       # the usual step: zero_grad(set_to_none=True) ran
+            for p, v in zip(live, views):
+                if p.requires_grad:
+                    p.grad = v
+            return views, True
+        bound = all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(live, views) if p.requires_grad)
+        if bound and self._overwrite_grads:                         # CUDA-graph replay: every step overwrites .grad
+            return views, True
+        # gradient accumulation (an earlier backward's result is still in .grad): compute into fresh tensors and let
+        # autograd add them
+        return [torch.empty_like(p) for p in params], False
+
+    _overwrite_grads = False   # set by train.GraphedTrainStep while it owns the step
 
     def set_dropout_scale(self, scale: Optional[torch.Tensor]) -> None:
         """Testing hook: force the (N, C0) Dropout3d channel scale used by the next training forwards."""

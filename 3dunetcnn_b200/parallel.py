@@ -29,10 +29,18 @@ class GradAllReduce:
     """Flat-bucket gradient averaging.  ``params`` are flattened into one contiguous fp32 buffer per call so the
     exchange is a single collective (96 MB at base_width 32: ~0.3 ms on NVSwitch)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, model=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.flat = None
+        self.model = model       # a UNet3D in flat-gradient mode: its bucket IS the exchange buffer (no copies)
+
+    def _reduce_mean(self, flat: torch.Tensor, world: int) -> None:
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)     # sum and 1/world in the collective
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(1.0 / world)
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
@@ -46,6 +54,12 @@ class GradAllReduce:
         world = dist.get_world_size(self.group)
         if world == 1:
             return
+        bucket = self.model.flat_gradient_bucket() if self.model is not None else None
+        if bucket is not None:
+            lo, hi = bucket.data_ptr(), bucket.data_ptr() + bucket.numel() * 4
+            if all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params):
+                self._reduce_mean(bucket, world)                              # gradients already live in the bucket
+                return
         grads = [p.grad for p in self.params if p.grad is not None]
         if not grads:
             return
@@ -59,8 +73,7 @@ class GradAllReduce:
             views.append(v)
             off += g.numel()
         torch._foreach_copy_(views, grads)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / world)
+        self._reduce_mean(self.flat, world)
         torch._foreach_copy_(grads, views)
 
 

@@ -7,10 +7,13 @@ and file output goes through a caller-supplied ``writer`` instead of ``monai.dat
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Callable, List, Optional, Sequence
 
 import torch
+
+from . import lib as _lib
 
 
 def _scan_starts(size: int, roi: int, overlap: float) -> List[int]:
@@ -33,41 +36,77 @@ def _gaussian_importance(roi: Sequence[int], device, sigma_scale: float = 0.125)
 
 
 class SlidingWindowInferer:
-    """``monai.inferers.SlidingWindowInferer(roi_size, sw_batch_size, overlap, mode)`` restated (parity unpinned)."""
+    """``monai.inferers.SlidingWindowInferer(roi_size, sw_batch_size, overlap, mode)`` restated (parity unpinned:
+    MONAI is absent from this image).  Tiling runs on the device through libb200unet: one gather kernel per tile batch
+    (volume -> [sw_batch, C, roi] NCDHW), the network, one importance-weighted scatter-accumulate kernel (tile order,
+    no atomics: deterministic), and a final normalisation by the precomputed weight sum of the scan."""
 
     def __init__(self, roi_size, sw_batch_size: int = 1, overlap: float = 0.25, mode: str = "constant", **unused):
         self.roi_size = tuple(int(r) for r in (roi_size if hasattr(roi_size, "__len__") else (roi_size,) * 3))
         self.sw_batch_size = int(sw_batch_size)
+        if not 1 <= self.sw_batch_size <= 16:
+            raise ValueError("sw_batch_size must be in 1..16")
         self.overlap = float(overlap)
         if mode not in ("constant", "gaussian"):
             raise ValueError("mode must be 'constant' or 'gaussian'")
         self.mode = mode
+        self._cache = {}
+
+    def _scan(self, shape, device):
+        """(roi, importance map, per-axis start lists, weight-sum volume) for this volume shape; cached."""
+        key = (tuple(shape), str(device))
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        D, H, W = shape
+        roi = [min(r, s) for r, s in zip(self.roi_size, (D, H, W))]
+        imp = (torch.ones(roi, device=device) if self.mode == "constant" else _gaussian_importance(roi, device)).contiguous()
+        axes = [_scan_starts(s, r, self.overlap) for s, r in zip((D, H, W), roi)]
+        dev_axes = [torch.tensor(a, dtype=torch.int32, device=device) for a in axes]
+        cnt = torch.empty((D, H, W), dtype=torch.float32, device=device)
+        lib = _lib.load_library()
+        with torch.cuda.device(device):
+            _lib.check(lib.b200unet_tiles_count(dev_axes[0].data_ptr(), len(axes[0]), dev_axes[1].data_ptr(), len(axes[1]),
+                                                dev_axes[2].data_ptr(), len(axes[2]), roi[0], roi[1], roi[2], imp.data_ptr(),
+                                                cnt.data_ptr(), D, H, W, _lib.stream_ptr()), "tiles_count")
+        self._cache = {key: (roi, imp, axes, cnt)}
+        return self._cache[key]
 
     def __call__(self, inputs: torch.Tensor, network: Callable, *args, **kwargs) -> torch.Tensor:
-        n, _, D, H, W = inputs.shape
-        roi = [min(r, s) for r, s in zip(self.roi_size, (D, H, W))]
-        dev = inputs.device
-        w = torch.ones(roi, device=dev) if self.mode == "constant" else _gaussian_importance(roi, dev)
-        starts = [(d, h, x) for d in _scan_starts(D, roi[0], self.overlap) for h in _scan_starts(H, roi[1], self.overlap)
-                  for x in _scan_starts(W, roi[2], self.overlap)]
+        if not inputs.is_cuda:
+            raise RuntimeError("SlidingWindowInferer tiles on the device (no CPU fallback); got %s" % inputs.device)
+        x = inputs.as_subclass(torch.Tensor) if type(inputs) is not torch.Tensor else inputs
+        x = x.detach().contiguous().float()
+        n, c, D, H, W = x.shape
+        dev = x.device
+        roi, imp, axes, cnt = self._scan((D, H, W), dev)
+        jobs = [(b, d, h, w) for b in range(n) for d in axes[0] for h in axes[1] for w in axes[2]]
+        lib = _lib.load_library()
+        B = self.sw_batch_size
+        tiles = torch.empty((B, c) + tuple(roi), dtype=torch.float32, device=dev)
         out = None
-        cnt = torch.zeros((1, 1, D, H, W), dtype=torch.float32, device=dev)
-        # tiles of all batch items are grouped so the plan sees a constant batch of sw_batch_size
-        jobs = [(b, s) for b in range(n) for s in starts]
-        for j0 in range(0, len(jobs), self.sw_batch_size):
-            chunk = jobs[j0:j0 + self.sw_batch_size]
-            patch = torch.stack([inputs[b, :, d:d + roi[0], h:h + roi[1], x:x + roi[2]] for b, (d, h, x) in chunk])
-            pad = self.sw_batch_size - len(chunk)
-            if pad:
-                patch = torch.cat([patch, patch[-1:].expand(pad, -1, -1, -1, -1)])
-            pred = network(patch.contiguous(), *args, **kwargs)
-            if out is None:
-                out = torch.zeros((n, pred.shape[1], D, H, W), dtype=torch.float32, device=dev)
-            for k, (b, (d, h, x)) in enumerate(chunk):
-                out[b, :, d:d + roi[0], h:h + roi[1], x:x + roi[2]] += pred[k].float() * w
-                if b == 0:
-                    cnt[0, :, d:d + roi[0], h:h + roi[1], x:x + roi[2]] += w
-        return out / cnt
+        with torch.cuda.device(dev):
+            for j0 in range(0, len(jobs), B):
+                chunk = jobs[j0:j0 + B]
+                padded = chunk + [chunk[-1]] * (B - len(chunk))    # the plan sees a constant batch of sw_batch_size
+                starts = (C.c_int32 * (4 * B))(*[v for job in padded for v in job])
+                _lib.check(lib.b200unet_tiles_gather(x.data_ptr(), n, c, D, H, W, starts, B, roi[0], roi[1], roi[2],
+                                                     tiles.data_ptr(), _lib.stream_ptr()), "tiles_gather")
+                pred = network(tiles, *args, **kwargs)
+                pred = pred.as_subclass(torch.Tensor) if type(pred) is not torch.Tensor else pred
+                if pred.requires_grad:
+                    raise RuntimeError("SlidingWindowInferer is inference-only (the reference uses it under torch.no_grad(): "
+                                       "training_utils.py:115-147, volumetric.py:140-148); call it inside torch.no_grad()")
+                pred = pred.contiguous().float()
+                if out is None:
+                    out = torch.zeros((n, pred.shape[1], D, H, W), dtype=torch.float32, device=dev)
+                starts = (C.c_int32 * (4 * len(chunk)))(*[v for job in chunk for v in job])
+                _lib.check(lib.b200unet_tiles_scatter(pred.data_ptr(), pred.shape[1], starts, len(chunk), roi[0], roi[1], roi[2],
+                                                      imp.data_ptr(), out.data_ptr(), n, D, H, W, _lib.stream_ptr()),
+                           "tiles_scatter")
+            _lib.check(lib.b200unet_tiles_normalize(out.data_ptr(), cnt.data_ptr(), n * out.shape[1], D * H * W,
+                                                    _lib.stream_ptr()), "tiles_normalize")
+        return out
 
 
 _INFERERS = {"SlidingWindowInferer": SlidingWindowInferer}

@@ -55,25 +55,186 @@ def batch_loss(model, images, target, criterion, n_gpus=0, use_amp=None, inferer
     return _batch_loss(model, images, target, criterion, inferer=inferer)
 
 
+class GraphedTrainStep:
+    """One training step -- forward, criterion, backward [, grad_sync], optimizer.step -- with the forward+loss+backward
+    part captured ONCE as a CUDA graph and replayed (training_utils.py:59-72 is what it replaces; shapes are static and
+    the plan is a fixed kernel list, so ~180 launches per step collapse into one graph launch).
+
+    ``step(images, target)`` accepts host (pinned or pageable) or device tensors: they are copied straight into the
+    graph's static input buffers (H2D lands in place, no staging copy) and the returned loss is the graph's static
+    0-dim tensor (read it with ``.item()`` when needed).  The model runs in flat-gradient mode: every replay overwrites
+    the ``.grad`` views of one persistent bucket, which ``grad_sync`` all-reduces in place.
+    """
+
+    def __init__(self, model, criterion, optimizer, images_shape, target_shape, target_dtype=torch.uint8, device=None,
+                 grad_sync=None, warmup: int = 2):
+        self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
+        device = device or next(model.parameters()).device
+        self.images = torch.zeros(tuple(images_shape), dtype=torch.float32, device=device)
+        self.target = torch.zeros(tuple(target_shape), dtype=target_dtype, device=device)
+        self.graph = None
+        self.loss = None
+        self.warmup = int(warmup)
+        self.device = device
+
+    def _capture(self):
+        model = self.model
+        model.train()
+        model.use_flat_gradients(True)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):            # plan creation, workspace, table uploads, bucket: outside the capture
+                self.optimizer.zero_grad(set_to_none=True)
+                loss = self.criterion(model(self.images), self.target)
+                loss.backward()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        model._overwrite_grads = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self.criterion(model(self.images), self.target)
+            self.loss.backward()
+
+    def step(self, images, target):
+        if self.graph is None:
+            self.images.copy_(images, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
+            self._capture()
+        self.images.copy_(images, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        params = self.model.ordered_parameters()
+        if params[0].grad is None:          # somebody ran zero_grad(set_to_none=True) since: re-bind the bucket views
+            for p, v in zip(params, self.model._grad_views):
+                if p.requires_grad:
+                    p.grad = v
+        if self.grad_sync is not None:
+            self.grad_sync()
+        self.optimizer.step()
+        return self.loss
+
+    __call__ = step
+
+    def matches(self, images, target) -> bool:
+        return tuple(images.shape) == tuple(self.images.shape) and tuple(target.shape) == tuple(self.target.shape)
+
+
+class DevicePrefetcher:
+    """Iterates a loader of ``{"image", "label"}`` items one batch ahead: the next batch's host->device copies run on a
+    side stream while the current step computes (the reference copies synchronously from pageable memory on the compute
+    stream: training_utils.py:89-91).  Pageable tensors still work, they just do not overlap."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream(device=device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, item):
+        with torch.cuda.stream(self.stream):
+            out = dict(item)
+            for k in ("image", "label"):
+                t = item[k]
+                out[k] = t if t.is_cuda else t.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ev)
+            for k in ("image", "label"):
+                cur[k].record_stream(main)
+            yield cur
+
+
+class _LaggedLoss:
+    """Reads step i's loss while step i+1 is already queued: an async D2H into pinned memory + an event per step
+    instead of ``loss.item()`` right after the launch (training_utils.py:63), which would drain the GPU every step."""
+
+    def __init__(self):
+        self.slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pending = []   # (slot, batch_size)
+        self.i = 0
+
+    def push(self, loss, batch_size):
+        k = self.i % 2
+        self.i += 1
+        self.slots[k].copy_(loss.detach(), non_blocking=True)
+        self.events[k].record()
+        self.pending.append((k, batch_size))
+
+    def pop_ready(self, keep: int):
+        out = []
+        while len(self.pending) > keep:
+            k, bs = self.pending.pop(0)
+            self.events[k].synchronize()
+            out.append((float(self.slots[k]), bs))
+        return out
+
+
+def _graphed_step_for(model, criterion, optimizer, images, target, grad_sync):
+    cache = model.__dict__.setdefault("_graphed_steps", {})
+    key = (tuple(images.shape), tuple(target.shape), target.dtype, id(criterion), id(optimizer), id(grad_sync))
+    step = cache.get(key)
+    if step is None:
+        step = cache[key] = GraphedTrainStep(model, criterion, optimizer, images.shape, target.shape,
+                                             target_dtype=target.dtype, grad_sync=grad_sync)
+    return step
+
+
 def epoch_training(train_loader, model, criterion, optimizer, epoch, n_gpus=None, print_frequency=1,
-                   print_gpu_memory=False, scaler=None, samples_per_epoch=None, iteration=1, grad_sync=None):
+                   print_gpu_memory=False, scaler=None, samples_per_epoch=None, iteration=1, grad_sync=None,
+                   use_cuda_graph=False):
     """training_utils.py:20-85.  ``grad_sync`` (optional callable) runs between backward and optimizer.step:
-    the data-parallel gradient all-reduce of ``parallel.GradAllReduce``."""
+    the data-parallel gradient all-reduce of ``parallel.GradAllReduce``.  ``use_cuda_graph``: replay the step through
+    ``GraphedTrainStep`` (kept on the model across epochs) for every batch of the first batch's shape; other shapes,
+    e.g. a short last batch, run eagerly.  On a GPU the loader is read one batch ahead (``DevicePrefetcher``) and the
+    loss of step i is read back while step i+1 runs, so the only host syncs are one step behind the queue."""
+    graphed = None
     batch_time = AverageMeter("Time", ":6.3f")
     data_time = AverageMeter("Data", ":6.3f")
     losses = AverageMeter("Loss", ":.4e")
     model.train()
+    on_gpu = n_gpus is not None and torch.cuda.is_available() and next(model.parameters()).is_cuda
+    loader = DevicePrefetcher(train_loader, next(model.parameters()).device) if on_gpu else train_loader
+    lag = _LaggedLoss() if on_gpu else None
     end = time.time()
-    for i, item in enumerate(train_loader):
+    batch_size = 0
+    for i, item in enumerate(loader):
         images, target = item["image"], item["label"]
         data_time.update(time.time() - end)
-        optimizer.zero_grad()
-        loss, batch_size = batch_loss(model, images, target, criterion, n_gpus=n_gpus, use_amp=scaler is not None)
-        loss.backward()
-        if grad_sync is not None:
-            grad_sync()
-        optimizer.step()
-        losses.update(loss.item(), batch_size)   # the only host sync of the step, after all work is queued
+        if use_cuda_graph and graphed is None:
+            graphed = _graphed_step_for(model, criterion, optimizer, images, target, grad_sync)
+        if graphed is not None and graphed.matches(images, target):
+            loss, batch_size = graphed(images, target), images.size(0)
+        else:
+            optimizer.zero_grad()            # (in flat-gradient mode the eager backward re-binds the same bucket views)
+            loss, batch_size = batch_loss(model, images, target, criterion, n_gpus=n_gpus, use_amp=scaler is not None)
+            loss.backward()
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+        if lag is not None:
+            lag.push(loss, batch_size)
+            for v, bs in lag.pop_ready(keep=1):
+                losses.update(v, bs)
+        else:
+            losses.update(loss.item(), batch_size)
         del loss
         batch_time.update(time.time() - end)
         end = time.time()
@@ -81,6 +242,9 @@ def epoch_training(train_loader, model, criterion, optimizer, epoch, n_gpus=None
             print("Epoch: [{}][{}/{}]\t{}\t{}\t{}".format(epoch, i + 1, len(train_loader), batch_time, data_time, losses))
         if samples_per_epoch and (i + 1) * batch_size >= samples_per_epoch:
             break
+    if lag is not None:
+        for v, bs in lag.pop_ready(keep=0):
+            losses.update(v, bs)
     return losses.avg
 
 

@@ -77,6 +77,8 @@ typedef struct b200unet_conv_desc {
   int32_t coef_ld;
   float slope;                  /* 0 = ReLU (myronenko.py:14), 0.01 = LeakyReLU (DynUNet blocks) */
   double* bstats;               /* mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat) */
+  int32_t cls_mode;             /* 1: data gradient of a k3 s2 p1 convolution (encoder downsampling, myronenko.py:103-105) without
+                                   zero insertion: x[0] = dY at half the extent of `out`, weights = the mode-1 pack; plain epilogue */
 } b200unet_conv_desc;
 int b200unet_conv3d(const b200unet_conv_desc* desc, void* stream);
 
@@ -106,13 +108,41 @@ int b200unet_head_bwd(const b200unet_tensor* x, const float* w, int n_out, const
                       const b200unet_tensor* dx, float* dw, void* stream);
 
 /* ---- Dice criterion (monai.losses.DiceLoss as configured by script_utils.py:61-77).
- * flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum.
+ * flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum,
+ * bit6 `target` points to fp32 values (soft labels) instead of uint8.
  * sums: [N][C][3] doubles (I, P, T) written by fwd and consumed by bwd. */
-int b200unet_dice_fwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+int b200unet_dice_fwd(const float* logits, const void* target, int n, int c, int64_t spatial, int flags,
                       float smooth_nr, float smooth_dr, double* sums, float* loss, void* stream);
-int b200unet_dice_bwd(const float* logits, const uint8_t* target, int n, int c, int64_t spatial, int flags,
+int b200unet_dice_bwd(const float* logits, const void* target, int n, int c, int64_t spatial, int flags,
                       float smooth_nr, float smooth_dr, const double* sums, const float* grad_out, float* dlogits,
                       void* stream);
+
+/* ---- sliding-window inference on the device (monai.inferers.SlidingWindowInferer as called by
+ * predict/volumetric.py:147-148 and train/training_utils.py:106-107).  `starts`: HOST array [ntiles][4] of
+ * (sample, d0, h0, w0), at most 16 tiles per call; volumes and tiles are NCDHW fp32.
+ *   gather:    tiles[b] = vol[sample_b, :, d0:d0+rd, h0:h0+rh, w0:w0+rw]
+ *   scatter:   out[sample_b, :, window_b] += pred[b] * importance   (tile order, deterministic: no atomics)
+ *   count:     cnt[d][h][w] = sum of `importance` over the full scan (separable DEVICE start lists per axis)
+ *   normalize: out[nc][v] /= cnt[v] */
+int b200unet_tiles_gather(const float* vol, int n, int c, int d, int h, int w, const int32_t* starts, int ntiles, int rd, int rh,
+                          int rw, float* tiles, void* stream);
+int b200unet_tiles_scatter(const float* pred, int c, const int32_t* starts, int ntiles, int rd, int rh, int rw,
+                           const float* importance, float* out, int n, int d, int h, int w, void* stream);
+int b200unet_tiles_count(const int32_t* starts_d, int nd, const int32_t* starts_h, int nh, const int32_t* starts_w, int nw, int rd,
+                         int rh, int rw, const float* importance, float* cnt, int d, int h, int w, void* stream);
+int b200unet_tiles_normalize(float* out, const float* cnt, int nc, int64_t spatial, void* stream);
+
+/* ---- the step before the path: label map -> one-hot uint8 target (utils/one_hot.py:7-37; `values`/`begin` are HOST
+ * arrays: channel c is 1 where isclose(round(data), values[k]) for any k in [begin[c], begin[c+1])), and z-score
+ * intensity normalisation (monai NormalizeIntensity selected by datasets/segmentation.py:77-87; `groups` = C when
+ * channel_wise else 1; stats: [groups][3] doubles of scratch). */
+int b200unet_one_hot(const float* data, int n, int64_t spatial, const float* values, const int32_t* begin, int n_channels,
+                     int do_round, uint8_t* y, void* stream);
+int b200unet_zscore(const float* x, int groups, int64_t spatial, int nonzero, double* stats, float* y, void* stream);
+/* ---- the step after the path: activation (0 none, 1 sigmoid, 2 softmax) + threshold -> int16 label map of ONE sample
+ * p [L][spatial] (utils/one_hot.py:46-118: label hierarchy, any/sum-then-threshold + argmax) */
+int b200unet_label_map(const float* p, int n_labels, int64_t spatial, const int32_t* labels, int act, float threshold,
+                       int hierarchy, int sum_then_threshold, int16_t* out, void* stream);
 
 /* ---- whole-network plan: UNet3D forward/backward (segmentation/unet.py:7-50, classification/myronenko.py,
  * classification/decoder.py:73-130, autoencoder/variational.py:37-87) as one schedule of the kernels above. */
@@ -127,6 +157,8 @@ typedef struct b200unet_net_desc {
   int32_t activation;         /* 0 none, 1 sigmoid, 2 softmax (variational.py:62-68) */
   int32_t split_precision;    /* 0 = bf16 single pass (perf), 1 = hi/lo split, 3 MMAs (parity) */
   int32_t batch, depth, height, width;
+  int32_t inference_only;     /* 1 = forward-only plan (volumetric.py:131-150 runs under no_grad): no backward schedule, no
+                                 backward buffers, forward temporaries are recycled -> a much smaller workspace */
 } b200unet_net_desc;
 
 typedef struct b200unet_plan b200unet_plan;
@@ -139,8 +171,8 @@ int b200unet_plan_num_params(const b200unet_plan* plan);
 int b200unet_plan_param_info(const b200unet_plan* plan, int i, int64_t shape[5], char* key, int key_cap);
 size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan);
 /* forward: x NCDHW fp32 -> logits NCDHW fp32.  params: device array-of-pointers (host array of device pointers) to
- * the fp32 parameters.  dropout_scale: [N][C0] per-channel scale or NULL (eval).  save_for_backward != 0 keeps the
- * activations needed by b200unet_plan_backward in `workspace`. */
+ * the fp32 parameters.  dropout_scale: [N][C0] per-channel scale or NULL (eval).  save_for_backward != 0 states that
+ * b200unet_plan_backward will follow (rejected on an inference_only plan, whose workspace keeps no activations). */
 int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
                           int save_for_backward, void* workspace, float* logits, void* stream);
 /* backward: dlogits NCDHW fp32 -> grads[i] (fp32, same shapes as params; overwritten). */

@@ -91,6 +91,41 @@ def test_conv3d_wide_inputs_on_halo_kernel(pkg, monkeypatch, cin, cout, dims, mo
     assert rel(stats[:, :cout].cpu(), s_ref) < (2e-3 if not split else 1e-4)
 
 
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("ci,co,dims", [(128, 128, (4, 16, 8)), (192, 256, (2, 16, 16)), (128, 96, (5, 16, 8))])
+def test_conv3d_wide_inputs_on_halo_kernel_gn_backward_epilogue(pkg, monkeypatch, ci, co, dims, split):
+    """The same wide-input halo dispatch with the mode-1 (GroupNorm/ReLU backward) epilogue: the data gradient of a
+    co -> ci ... convolution seen from its output side, i.e. K = co >= 128 input channels of the GEMM."""
+    monkeypatch.setenv("B200UNET_HALO_WIDE_MIN", "0")
+    L = pkg.lib
+    torch.manual_seed(ci + 2 * co)
+    n, G = 2, 8
+    dyv = torch.randn(n, co, *dims, device=DEV)
+    xv = torch.randn(n, ci, *dims, device=DEV) + 0.3
+    w = torch.randn(co, ci, 3, 3, 3, device=DEV) / (ci * 27) ** 0.5
+    gamma, beta = torch.randn(ci, device=DEV) * 0.3 + 1, torch.randn(ci, device=DEV) * 0.2
+    dy, x = L.Act.from_ncdhw(dyv, split=split), L.Act.from_ncdhw(xv, split=split)
+    wdh, wdl, _, _, _ = L.pack_weights(w, 1, split=split)
+    _, _, _, _, wq = _packed_to_torch(L, w, 0, split, co, ci, 3)
+    S = dims[0] * dims[1] * dims[2]
+    stats = torch.zeros(n, ci, 2, dtype=torch.float64, device=DEV)
+    L.channel_stats(x, stats, ci)
+    coef = torch.empty(n, ci, 4, device=DEV)
+    L.gn_finalize(stats, gamma, beta, n, ci, ci, G, S, 1e-5, coef)
+    bst = torch.zeros(n, ci, 2, dtype=torch.float64, device=DEV)
+    dz = L.Act.empty(n, *dims, ci, split=split)
+    L.conv3d(dy, wdh, wdl, 3, 1, dz, ci, co, mode=1, gn_x=x, coef=coef, coef_ld=ci, bstats=bst)
+    xq = x.to_ncdhw(ci).double().cpu().requires_grad_(True)
+    z = F.group_norm(xq, G, gamma.double().cpu(), beta.double().cpu(), 1e-5)
+    z.retain_grad()
+    F.conv3d(F.relu(z), wq, padding=1).backward(dy.to_ncdhw(co).double().cpu())
+    assert rel(dz.to_ncdhw(ci), z.grad) < TOL_STORE[split] * 1.5
+    mu, rstd = coef[..., 2].double().cpu(), coef[..., 3].double().cpu()
+    xhat = (xq.detach() - mu[:, :, None, None, None]) * rstd[:, :, None, None, None]
+    b_ref = torch.stack([z.grad.sum(dim=(2, 3, 4)), (z.grad * xhat).sum(dim=(2, 3, 4))], dim=-1)
+    assert rel(bst, b_ref) < (2e-3 if not split else 1e-4)
+
+
 @pytest.mark.parametrize("cin,cout,r", [(32, 32, 64), (64, 64, 48), (64, 128, 32), (32, 64, 64), (128, 128, 32)])
 def test_conv3d_outputs_are_bitwise_repeatable(pkg, cin, cout, r):
     """Race detector: the stored activations involve no atomics, so repeated launches on identical inputs must agree
@@ -216,6 +251,33 @@ def test_conv3d_dgrad_groupnorm_relu_backward_epilogue(pkg, split, D):
     xhat = (xq.detach() - mu[:, :, None, None, None]) * rstd[:, :, None, None, None]
     b_ref = torch.stack([z.grad.sum(dim=(2, 3, 4)), (z.grad * xhat).sum(dim=(2, 3, 4))], dim=-1)
     assert rel(bst, b_ref) < 1e-4
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("ci,co,odims", [(32, 32, (8, 8, 8)), (64, 64, (4, 8, 16)), (128, 128, (4, 4, 8)), (16, 24, (3, 5, 6)),
+                                         (32, 32, (16, 16, 16))])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_stride2_data_gradient_by_parity_classes(pkg, ci, co, odims, with_res, split):
+    """dX of a 3x3x3 stride-2 padding-1 convolution (encoder downsampling, myronenko.py:103-105) computed as eight
+    parity-class implicit GEMMs over the un-inserted dY (cls_mode=1), (+ residual, * dropout scale), against autograd."""
+    L = pkg.lib
+    torch.manual_seed(ci + co + odims[0])
+    n = 2
+    idims = tuple(2 * d for d in odims)
+    w = torch.randn(co, ci, 3, 3, 3, device=DEV) / (ci * 27) ** 0.5
+    dy = L.Act.from_ncdhw(torch.randn(n, co, *odims, device=DEV), split=split)
+    wdh, wdl, _, _, _ = L.pack_weights(w, 1, split=split)                 # [T][Cip][Cop], taps flipped
+    _, _, cop, cip, wq = _packed_to_torch(L, w, 0, split, co, ci, 3)
+    dx = L.Act.empty(n, *idims, cip, split=split, zero=True)
+    res = L.Act.from_ncdhw(torch.randn(n, ci, *idims, device=DEV), split=split) if with_res else None
+    scale = (torch.rand(n, cip, device=DEV) + 0.5) if with_res else None
+    L.conv3d(dy, wdh, wdl, 3, 1, dx, cip, cop, res=res, scale=scale, cls_mode=1)
+    xq = torch.zeros(n, ci, *idims, dtype=torch.float64, requires_grad=True)
+    F.conv3d(xq, wq, stride=2, padding=1).backward(dy.to_ncdhw(co).double().cpu())
+    ref = xq.grad
+    if with_res:
+        ref = (ref + res.to_ncdhw(ci).double().cpu()) * scale[:, :ci].double().cpu()[:, :, None, None, None]
+    assert rel(dx.to_ncdhw(ci), ref) < TOL_STORE[split] * 1.5
 
 
 @pytest.mark.parametrize("split", [False, True])
