@@ -65,6 +65,7 @@ int b200unet_conv3d(const b200unet_conv_desc* d, void* stream) {
     op.src[s].w_hi = reinterpret_cast<const bf16*>(d->w_hi[s]);
     op.src[s].w_lo = reinterpret_cast<const bf16*>(d->w_lo[s]);
     op.src[s].ksz = d->ksz[s]; op.src[s].stride = d->stride[s]; op.src[s].Cip = d->cip[s];
+    op.src[s].nopad = d->ksz[s] == 2 ? 1 : 0;   // kernel 2 = the unpadded kernel = stride case
   }
   op.Cop = d->cop;
   op.out = to_act(&d->out);
@@ -81,7 +82,7 @@ int b200unet_conv3d_wgrad(const b200unet_tensor* a, const b200unet_tensor* dy, i
                           float* dw, void* stream) {
   NOT_NULL(a); NOT_NULL(dy); NOT_NULL(dw);
   WgradOp op;
-  op.a = to_act(a); op.dy = to_act(dy); op.ksz = ksz; op.stride = stride; op.Cip = cip; op.Cop = cop; op.dw = dw;
+  op.a = to_act(a); op.dy = to_act(dy); op.ksz = ksz; op.stride = stride; op.nopad = ksz == 2 ? 1 : 0; op.Cip = cip; op.Cop = cop; op.dw = dw;
   return launch_wgrad(op, to_stream(stream));
 }
 
@@ -119,6 +120,14 @@ int b200unet_gn_bwd(const b200unet_tensor* dz, const b200unet_tensor* x, const f
   if (add2) a2 = to_act(add2);
   return launch_gn_bwd(to_act(dz), to_act(x), coef, coef2, add1 ? &a1 : nullptr, add2 ? &a2 : nullptr, to_act(dx),
                        nullptr, to_stream(stream));
+}
+
+int b200unet_act_bwd(const b200unet_tensor* g1, const b200unet_tensor* g2, const b200unet_tensor* c, const float* coef, float slope,
+                     const b200unet_tensor* dz, double* bstats, int bstats_ld, void* stream) {
+  NOT_NULL(g1); NOT_NULL(c); NOT_NULL(coef); NOT_NULL(dz); NOT_NULL(bstats);
+  Act a2;
+  if (g2) a2 = to_act(g2);
+  return launch_act_bwd(to_act(g1), g2 ? &a2 : nullptr, to_act(c), coef, slope, to_act(dz), bstats, bstats_ld, to_stream(stream));
 }
 
 int b200unet_upsample2x_fwd(const b200unet_tensor* x, const b200unet_tensor* y, double* stats, int stats_ld,

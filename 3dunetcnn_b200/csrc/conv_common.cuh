@@ -31,7 +31,7 @@ struct ConvArgs {
   int N, Do, Ho, Wo, Cout;
   int tw, th, td;
   int tiles_w, tiles_h, tiles_d;
-  int ntaps[2], ksz[2], kchunks[2], stride[2];
+  int ntaps[2], ksz[2], kchunks[2], stride[2], pad[2];
   int npass;
   int mode;
   bf16* out_hi; bf16* out_lo; int ldo;

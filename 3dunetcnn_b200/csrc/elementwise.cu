@@ -539,6 +539,107 @@ int launch_gn_bwd_fused(const Act& dz, const Act& x, const float* coef, const do
   return launch_gn_bwd_impl(dz, x, coef, nullptr, add1, add2, dx, scale, &f, st);
 }
 
+// ------------------------------------------------------------------------------------------------ activation backward (+ statistics)
+// Post-activation blocks (conv -> norm -> act: MONAI UnetBasicBlock, the model examples/brats2020/brats2020_config.json
+// trains): the gradient arriving at a block output is that of the ACTIVATED tensor a = act(A c + B), c = the
+// convolution output.   dz = (g1 [+ g2]) * act'(A c + B);   bstats[n][ch] += (sum dz, sum dz * xhat),  xhat = (c - mu) rstd
+// which is exactly what the GroupNorm backward (k_gn_bwd) consumes.  Same thread <-> channel-chunk mapping as k_gn_apply.
+__global__ void __launch_bounds__(256) k_act_bwd(Act g1, Act g2, Act c, const float4* __restrict__ coef, float slope, Act dz,
+                                                 double* __restrict__ bstats, int bstats_ld) {
+  extern __shared__ double smb[];   // [C][2]
+  for (int i = threadIdx.x; i < c.C * 2; i += blockDim.x) smb[i] = 0.0;
+  __syncthreads();
+  const int c8n = c.C / 8;
+  const int n = blockIdx.y;
+  const long long S = (long long)c.D * c.H * c.W;
+  const int c8 = threadIdx.x % c8n;
+  const int vslot = threadIdx.x / c8n, vper = blockDim.x / c8n;
+  float ka[8], kb[8], km[8], kr[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = __ldg(coef + (long long)n * c.C + c8 * 8 + j);
+    ka[j] = k.x; kb[j] = k.y; km[j] = k.z; kr[j] = k.w;
+    s1[j] = s2[j] = 0.f;
+  }
+  const long long base = (long long)n * S;
+  for (long long s = (long long)blockIdx.x * vper + vslot; s < S; s += (long long)gridDim.x * vper) {
+    float g[8], x[8];
+    load8(g1.hi, g1.lo, (base + s) * g1.ld + c8 * 8, g);
+    load8(c.hi, c.lo, (base + s) * c.ld + c8 * 8, x);
+    if (g2.hi) {
+      float h[8];
+      load8(g2.hi, g2.lo, (base + s) * g2.ld + c8 * 8, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += h[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(ka[j], x[j], kb[j]);
+      const float d = z > 0.f ? g[j] : g[j] * slope;
+      g[j] = d;
+      s1[j] += d;
+      s2[j] = fmaf(d, (x[j] - km[j]) * kr[j], s2[j]);
+    }
+    store8(dz.hi, dz.lo, (base + s) * dz.ld + c8 * 8, g);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&smb[(c8 * 8 + j) * 2 + 0], (double)s1[j]);
+    atomicAdd(&smb[(c8 * 8 + j) * 2 + 1], (double)s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c.C * 2; i += blockDim.x) atomicAdd(&bstats[(long long)n * bstats_ld * 2 + i], smb[i]);
+}
+
+int launch_act_bwd(const Act& g1, const Act* g2, const Act& c, const float* coef, float slope, const Act& dz, double* bstats,
+                   int bstats_ld, cudaStream_t st) {
+  B200_REQUIRE(c.C % 8 == 0 && g1.C == c.C && dz.C == c.C && (!g2 || g2->C == c.C), E_INVALID, "act_bwd: channel mismatch");
+  B200_REQUIRE(coef && bstats, E_INVALID, "act_bwd: null argument");
+  const int c8n = c.C / 8;
+  const int threads = ew_threads_for(c8n);
+  B200_REQUIRE(threads <= 256, E_UNSUPPORTED, "act_bwd: C=%d unsupported", c.C);
+  const long long S = (long long)c.D * c.H * c.W;
+  const int vper = threads / c8n;
+  long long want = (S + vper - 1) / vper;
+  const long long cap = (148LL * 4 + c.N - 1) / c.N;
+  const int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  Act none = make_act(nullptr, nullptr, 0, 0, 0, 0, 0, 0);
+  k_act_bwd<<<dim3(blocks, c.N), threads, c.C * 2 * sizeof(double), st>>>(g1, g2 ? *g2 : none, c, reinterpret_cast<const float4*>(coef),
+                                                                          slope, dz, bstats, bstats_ld);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+// dbias[o] = sum over n, voxels of dlogits[n][o][s]   (bias of the 1x1x1 output block, MONAI UnetOutBlock)
+__global__ void k_head_dbias(const float* __restrict__ dlogits, int N, int NO, long long S, float* __restrict__ dbias) {
+  __shared__ double sh[32];
+  const int o = blockIdx.y;
+  double acc = 0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = dlogits + ((long long)n * NO + o) * S;
+    float a = 0.f;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) a += p[s];
+    acc += (double)a;
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(&dbias[o], (float)t);
+  }
+}
+
+int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st) {
+  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * NO, st));
+  long long want = (S + 255) / 256;
+  const int blocks = (int)(want < 128 ? (want > 0 ? want : 1) : 128);
+  k_head_dbias<<<dim3(blocks, NO), 256, 0, st>>>(dlogits, N, NO, S, dbias);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
 // ------------------------------------------------------------------------------------------------ element-wise add (y = a + b)
 __global__ void k_add(Act a, Act b, Act y) {
   const int c8n = a.C / 8;
@@ -705,6 +806,7 @@ __global__ void k_upsample2x_bwd(Act dy, Act dx) {
 int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st) {
   B200_REQUIRE(dx.C % 8 == 0 && dy.C == dx.C, E_INVALID, "upsample_bwd: channel mismatch");
   B200_REQUIRE(dy.D == 2 * dx.D && dy.H == 2 * dx.H && dy.W == 2 * dx.W, E_UNSUPPORTED, "upsample_bwd: not 2x");
+  if (use_tiled_upsample_bwd()) return launch_upsample2x_bwd_tiled(dy, dx, st);
   long long total = dx.voxels() * (dx.C / 8);
   k_upsample2x_bwd<<<ew_blocks(total, 256), 256, 0, st>>>(dy, dx);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -713,7 +815,8 @@ int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ head: 1x1x1 conv C -> n_out
 // logits NCDHW fp32 (the reference-facing layout).  One thread per voxel; weights in shared memory.
-__global__ void k_head_fwd(Act x, const float* __restrict__ w, int n_out, int act_mode, float* __restrict__ logits) {
+__global__ void k_head_fwd(Act x, const float* __restrict__ w, const float* __restrict__ bias, int n_out, int act_mode,
+                           float* __restrict__ logits) {
   extern __shared__ float sw[];  // [n_out][C]
   for (int i = threadIdx.x; i < n_out * x.C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -724,7 +827,7 @@ __global__ void k_head_fwd(Act x, const float* __restrict__ w, int n_out, int ac
     const long long s = v % S;
     float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int o = 0; o < 8; ++o) acc[o] = (bias && o < n_out) ? __ldg(bias + o) : 0.f;
     for (int c0 = 0; c0 < x.C; c0 += 8) {
       float u[8];
       load8(x.hi, x.lo, v * x.ld + c0, u);
@@ -750,10 +853,10 @@ __global__ void k_head_fwd(Act x, const float* __restrict__ w, int n_out, int ac
   }
 }
 
-int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st) {
+int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st, const float* bias) {
   B200_REQUIRE(n_out >= 1 && n_out <= 8, E_UNSUPPORTED, "head: n_outputs=%d > 8 unsupported", n_out);
   B200_REQUIRE(x.C % 8 == 0, E_INVALID, "head: C=%d", x.C);
-  k_head_fwd<<<ew_blocks(x.voxels(), 256), 256, n_out * x.C * sizeof(float), st>>>(x, w, n_out, act_mode, logits);
+  k_head_fwd<<<ew_blocks(x.voxels(), 256), 256, n_out * x.C * sizeof(float), st>>>(x, w, bias, n_out, act_mode, logits);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -783,25 +886,42 @@ __global__ void k_head_bwd(Act x, const float* __restrict__ w, const float* __re
   for (int o = 0; o < NO; ++o)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[o][j] = sw[o * x.C + c8 * 8 + j];
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long v = t / c8n;
-    const int n = (int)(v / S);
-    const long long s = v % S;
-    float g[NO];
+  // UF voxels in flight per thread (all loads of an iteration are issued before the first FMA): with one voxel per
+  // iteration the kernel ran at ~40% of the HBM rate (register-limited occupancy, one 16-byte load in flight per thread)
+  constexpr int UF = 4;
+  const long long tstride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += UF * tstride) {
+    float g[UF][NO], u[UF][8];
+    bool ok[UF];
 #pragma unroll
-    for (int o = 0; o < NO; ++o) g[o] = __ldg(dlogits + ((long long)n * NO + o) * S + s);
-    float u[8], d[8];
-    load8(x.hi, x.lo, v * x.ld + c8 * 8, u);
+    for (int q = 0; q < UF; ++q) {
+      const long long t = t0 + q * tstride;
+      ok[q] = t < total;
+      if (ok[q]) {
+        const long long v = t / c8n;
+        const int n = (int)(v / S);
+        const long long s = v % S;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = 0.f;
-#pragma unroll
-    for (int o = 0; o < NO; ++o)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d[j] = fmaf(g[o], wr[o][j], d[j]);
-        pdw[o][j] = fmaf(g[o], u[j], pdw[o][j]);
+        for (int o = 0; o < NO; ++o) g[q][o] = __ldg(dlogits + ((long long)n * NO + o) * S + s);
+        load8(x.hi, x.lo, v * x.ld + c8 * 8, u[q]);
       }
-    store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
+    }
+#pragma unroll
+    for (int q = 0; q < UF; ++q) {
+      if (!ok[q]) continue;
+      const long long v = (t0 + q * tstride) / c8n;
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = 0.f;
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          d[j] = fmaf(g[q][o], wr[o][j], d[j]);
+          pdw[o][j] = fmaf(g[q][o], u[q][j], pdw[o][j]);
+        }
+      store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
+    }
   }
   // lanes l and l' share the chunk iff l % c8n == l' % c8n (c8n is a power of two <= 32 here, else fall back to atomics)
   const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
@@ -856,15 +976,14 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Co, int Ci, int 
   const long long total = (long long)T * Cop * Cip;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2 || mode == 4) {   // forward layout [T][Cop][Cip]
       const int ci = (int)(i % Cip); const int co = (int)((i / Cip) % Cop); const int t = (int)(i / ((long long)Cip * Cop));
-      if (ci < Ci && co < Co) v = w[((long long)co * Ci + ci) * T + t];
-    } else if (mode == 1) {
+      if (ci < Ci && co < Co)
+        v = mode == 0 ? w[((long long)co * Ci + ci) * T + t] : w[((long long)ci * Co + co) * T + (mode == 2 ? T - 1 - t : t)];
+    } else {                                     // data-gradient layout [T][Cip][Cop]
       const int co = (int)(i % Cop); const int ci = (int)((i / Cop) % Cip); const int t = (int)(i / ((long long)Cip * Cop));
-      if (ci < Ci && co < Co) v = w[((long long)co * Ci + ci) * T + (T - 1 - t)];
-    } else {
-      const int ci = (int)(i % Cip); const int co = (int)((i / Cip) % Cop); const int t = (int)(i / ((long long)Cip * Cop));
-      if (ci < Ci && co < Co) v = w[((long long)ci * Co + co) * T + (T - 1 - t)];
+      if (ci < Ci && co < Co)
+        v = mode == 1 ? w[((long long)co * Ci + ci) * T + (T - 1 - t)] : w[((long long)ci * Co + co) * T + t];
     }
     bf16 h = __float2bfloat16_rn(v);
     hi[i] = h;
@@ -914,10 +1033,11 @@ __global__ void k_pack_all(PtrTable params, const PackJob* __restrict__ jobs, ui
   const long long total = (long long)j.T * j.Cop * j.Cip;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (j.mode == 0 || j.mode == 2) {
+    if (j.mode == 0 || j.mode == 2 || j.mode == 4) {
       const int ci = (int)(i % j.Cip); const int co = (int)((i / j.Cip) % j.Cop); const int t = (int)(i / ((long long)j.Cip * j.Cop));
       if (ci < j.Ci && co < j.Co)
-        v = j.mode == 0 ? w[((long long)co * j.Ci + ci) * j.T + t] : w[((long long)ci * j.Co + co) * j.T + (j.T - 1 - t)];
+        v = j.mode == 0 ? w[((long long)co * j.Ci + ci) * j.T + t]
+                        : w[((long long)ci * j.Co + co) * j.T + (j.mode == 2 ? j.T - 1 - t : t)];
     } else {
       const int co = (int)(i % j.Cop); const int ci = (int)((i / j.Cop) % j.Cip); const int t = (int)(i / ((long long)j.Cip * j.Cop));
       if (ci < j.Ci && co < j.Co)
@@ -931,6 +1051,7 @@ __global__ void k_pack_all(PtrTable params, const PackJob* __restrict__ jobs, ui
 
 int launch_pack_all(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st) {
   if (njobs == 0) return OK;
+  if (use_tiled_pack()) return launch_pack_all_tiled(params, jobs_dev, njobs, ws, split, st);
   k_pack_all<<<dim3(48, njobs), 256, 0, st>>>(params, jobs_dev, ws, split ? 1 : 0);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
@@ -954,6 +1075,7 @@ __global__ void k_unpack_all(PtrTable grads, const PackJob* __restrict__ jobs, c
 
 int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st) {
   if (njobs == 0) return OK;
+  if (use_tiled_pack()) return launch_unpack_all_tiled(grads, jobs_dev, njobs, ws, st);
   k_unpack_all<<<dim3(48, njobs), 256, 0, st>>>(grads, jobs_dev, ws);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
       for (int src = 0; src < 2; ++src) {
         const int nt = p.ntaps[src];
         if (nt == 0) continue;
-        const int ks = p.ksz[src], pad = ks >> 1, sd = p.stride[src];
+        const int ks = p.ksz[src], pad = p.pad[src], sd = p.stride[src];
         const int ntap_loop = p.cls_mode ? (int)p.cls_n[cls] : nt;
         for (int ti = 0; ti < ntap_loop; ++ti) {
           int tap = ti, cw, ch, cd;
@@ -268,15 +268,16 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
   bool split = false;
   for (int s = 0; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
-    B200_REQUIRE(c.ksz == 1 || c.ksz == 3, E_UNSUPPORTED, "igemm_conv: kernel_size=%d unsupported", c.ksz);
+    B200_REQUIRE(c.ksz == 1 || c.ksz == 3 || (c.ksz == 2 && c.nopad && (c.stride == 2 || op.cls_mode == 2)), E_UNSUPPORTED,
+                 "igemm_conv: kernel_size=%d unsupported", c.ksz);
     B200_REQUIRE(c.stride == 1 || c.stride == 2, E_UNSUPPORTED, "igemm_conv: stride=%d unsupported", c.stride);
     B200_REQUIRE(c.x.C % 8 == 0 && c.x.ld % 8 == 0, E_UNSUPPORTED, "igemm_conv: Cin=%d must be a multiple of 8", c.x.C);
     B200_REQUIRE(c.x.N == out.N, E_INVALID, "igemm_conv: batch mismatch");
-    const int pad = c.ksz / 2;
+    const int pad = c.nopad ? 0 : c.ksz / 2;
     if (op.cls_mode)
-      B200_REQUIRE(op.nsrc == 1 && c.ksz == 3 && 2 * c.x.D == out.D && 2 * c.x.H == out.H && 2 * c.x.W == out.W && op.mode == 0 &&
-                       !op.stats && !op.bias && !op.zero_last,
-                   E_INVALID, "igemm_conv: class mode needs one 3x3x3 source at half the output extent and a plain epilogue");
+      B200_REQUIRE(op.nsrc == 1 && c.ksz == (op.cls_mode == 2 ? 2 : 3) && 2 * c.x.D == out.D && 2 * c.x.H == out.H && 2 * c.x.W == out.W &&
+                       op.mode == 0 && !op.bias && !op.zero_last,
+                   E_INVALID, "igemm_conv: class mode needs one source at half the output extent and a plain epilogue");
     else
     B200_REQUIRE((c.x.D + 2 * pad - c.ksz) / c.stride + 1 == out.D && (c.x.H + 2 * pad - c.ksz) / c.stride + 1 == out.H &&
                      (c.x.W + 2 * pad - c.ksz) / c.stride + 1 == out.W,
@@ -294,7 +295,7 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
   const Swz swz = swz_for_bytes(KC * 2);
   for (int s = 0; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
-    a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = c.stride;
+    a.ntaps[s] = c.ksz * c.ksz * c.ksz; a.ksz[s] = c.ksz; a.stride[s] = c.stride; a.pad[s] = c.nopad ? 0 : c.ksz / 2;
     a.kchunks[s] = ceil_div(c.x.C, KC);
     const int estride = op.cls_mode ? 1 : c.stride;
     B200_TRY(make_act_map(&maps.a[s][0], c.x.hi, c.x.N, c.x.D, c.x.H, c.x.W, c.x.C, c.x.ld, KC, a.tw, a.th, a.td,
@@ -316,11 +317,14 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     // data gradient of y[o] = sum_k x[2o + k - 1] w[k]: dx[2j] = dy[j] w[1]; dx[2j+1] = dy[j] w[2] + dy[j+1] w[0].  With the
     // flipped pack Wd[k'] = w[2 - k'] (what emit_dgrad binds): even outputs use k' = 1 (delta 0), odd outputs k' = 0
     // (delta 0) and k' = 2 (delta +1); dy[j+1] beyond the grid reads as zero (TMA out-of-bounds fill).
-    a.cls_mode = 1;
+    // cls_mode 2 (ConvTranspose3d, kernel = stride = 2): out[2j + p] = x[j] w[p], one tap per class
+    a.cls_mode = op.cls_mode;
     const int cbo = BN < 64 ? BN : 64;
     for (int cls = 0; cls < 8; ++cls) {
       const int pd = (cls >> 2) & 1, ph = (cls >> 1) & 1, pw = cls & 1;
       int n = 0;
+      if (op.cls_mode == 2) a.cls_tap[cls][n++] = (unsigned char)cls;   // tap index kd*4 + kh*2 + kw = the class itself
+      else
       for (int kd = 0; kd < 3; ++kd)
         for (int kh = 0; kh < 3; ++kh)
           for (int kw = 0; kw < 3; ++kw) {

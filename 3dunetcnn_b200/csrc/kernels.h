@@ -22,7 +22,14 @@ int launch_gn_bwd(const Act& dz, const Act& x, const float* coef, const float* c
 int launch_add(const Act& a, const Act& b, const Act& y, cudaStream_t st);
 int launch_upsample2x_fwd(const Act& x, const Act& y, double* stats, int stats_ld, cudaStream_t st);
 int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st);
-int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st);
+bool use_tiled_upsample_bwd();
+int launch_upsample2x_bwd_tiled(const Act& dy, const Act& dx, cudaStream_t st);
+int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st,
+                    const float* bias = nullptr);
+int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st);
+// post-activation blocks: dz = (g1 [+ g2]) * act'(A c + B), bstats += (sum dz, sum dz*xhat)
+int launch_act_bwd(const Act& g1, const Act* g2, const Act& c, const float* coef, float slope, const Act& dz, double* bstats,
+                   int bstats_ld, cudaStream_t st);
 int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
                     cudaStream_t st);
 int launch_pack_weights(const float* w, int Co, int Ci, int Cop, int Cip, int T, int mode, bf16* hi, bf16* lo,
@@ -35,12 +42,17 @@ struct PackJob {
   int pidx;                 // index into the parameter / gradient pointer table
   int Co, Ci, Cop, Cip, T;
   int mode;                 // 0 forward [T][Cop][Cip], 1 data-gradient [T][Cip][Cop] flipped; ConvTranspose3d weight
-                            // [Ci][Co][T]: 2 forward [T][Cop][Cip] flipped, 3 data-gradient [T][Cip][Cop] unflipped;
+                            // [Ci][Co][T]: 2 forward [T][Cop][Cip] flipped, 3 data-gradient [T][Cip][Cop] unflipped,
+                            // 4 forward [T][Cop][Cip] unflipped (kernel = stride ConvTranspose3d: out[2j+p] = x[j] w[p]);
                             // unpack: 0 -> [Co][Ci][T], 2 -> [Ci][Co][T] flipped
   long long off_hi, off_lo; // workspace byte offsets (unpack: off_hi = fp32 accumulator)
 };
 int launch_pack_all(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st);
 int launch_unpack_all(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st);
+// shared-memory tiled / register-tiled rewrites (small_ops.cu); selected unless B200UNET_OLD_SMALL_OPS is set
+bool use_tiled_pack();
+int launch_pack_all_tiled(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st);
+int launch_unpack_all_tiled(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st);
 int launch_bias_grad(const Act& dy, float* dbias, cudaStream_t st);   // dbias[c] = sum over the VISIBLE voxels of dy
 int launch_zero_insert(const Act& x, const Act& z, int od, int oh, int ow, cudaStream_t st);
 int launch_ncdhw_to_act(const float* x, int C, const Act& out, cudaStream_t st);
@@ -79,7 +91,8 @@ struct ConvSrc {
   Act x;               // A operand (NDHWC bf16, hi[/lo])
   const bf16* w_hi;    // packed weights [T][Cop][Cip] (K = Cip contiguous)
   const bf16* w_lo;    // nullptr in single-pass mode
-  int ksz;             // 1 or 3
+  int ksz;             // 1 or 3 (2 with nopad: the kernel = stride = 2 case of MONAI's UnetUpBlock transposed convolution)
+  int nopad;           // 0: padding = ksz / 2 (resnet.py:12-22); 1: no padding
   int stride;          // 1 or 2 (spatial traversal stride on x)
   int Cip;             // packed K extent of the weights (>= x.C, multiple of 8)
 };
@@ -101,7 +114,8 @@ struct ConvOp {
   double* bstats;      // mode 1: [N][coef_ld][2] += (sum dz, sum dz*xhat)
   const float* bias;   // mode 0: optional per-channel bias
   int zero_last;       // mode 0: output voxels on the high boundary of each axis are forced to 0
-  int cls_mode;        // 1: data gradient of a 3x3x3 stride-2 padding-1 convolution WITHOUT zero insertion: src[0].x = dY (low
+  int cls_mode;        // 2: ConvTranspose3d(kernel = stride = 2) forward: src[0].x = input at half the output extent, src[0].w = the
+                       // mode-4 pack [8][Cop][Cip]; class p = one tap.  1: data gradient of a 3x3x3 stride-2 padding-1 convolution WITHOUT zero insertion: src[0].x = dY (low
                        // resolution), src[0].w = the flipped data-gradient pack, out = dX at twice the extent; eight
                        // parity-class implicit GEMMs (27 tap products in total instead of 8 x 27) in one launch
 };
@@ -115,8 +129,9 @@ int launch_conv_halo(const ConvOp& op, int num_sms, cudaStream_t st);
 struct WgradOp {
   Act a;       // conv input (normalised activation), NDHWC
   Act dy;      // gradient of the conv output, NDHWC (dims = conv output dims)
-  int ksz;     // 1 or 3
+  int ksz;     // 1 or 3 (2 with nopad)
   int stride;  // 1 or 2
+  int nopad;   // 0: padding = ksz / 2; 1: no padding
   int Cip;     // pitch of the [T][Cip][Cop] fp32 accumulator rows
   int Cop;
   float* dw;   // fp32 [T][Cip][Cop]; accumulated with atomics, caller zero-fills
@@ -124,6 +139,8 @@ struct WgradOp {
 int launch_wgrad(const WgradOp& op, cudaStream_t st);              // dispatcher: halo-resident kernel when eligible
 int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st);
 bool wgrad_halo_eligible(const WgradOp& op);
+bool wgrad_1x1_narrow_eligible(const WgradOp& op);              // 1x1x1, <= 16 input channels: SIMT register tile
+int launch_wgrad_1x1_narrow(const WgradOp& op, cudaStream_t st);
 int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st);
 
 // ---- descriptor-semantics probe (probe.cu)

@@ -73,6 +73,7 @@ struct ConvLayer {
   size_t dw;               // fp32 accumulator         [T][Cip][Cop]
   bool need_dgrad;
   bool transposed;         // nn.ConvTranspose3d weight [Ci][Co][T] (+ bias parameter pb)
+  bool up2;                // ConvTranspose3d with kernel = stride = 2 (MONAI UnetUpBlock): T = 8, weight [Ci][Co][8], no padding
   int pb;
   std::string name;        // state-dict key (profiling labels)
 };
@@ -133,6 +134,7 @@ struct b200unet_plan {
   double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
   bool have_drop = false;
+  float slope = 0.f;        // negative slope of the activation (0 = ReLU: UNet3D; 0.01 = LeakyReLU: DynUNet)
   bool infer = false;       // forward-only plan: no backward schedule / buffers, forward temporaries are recycled
   std::vector<std::pair<size_t, std::pair<size_t, size_t>>> free_bufs;   // (bytes, (off_hi, off_lo)) of released buffers
 
@@ -309,6 +311,7 @@ static int new_conv(Plan& P, const std::string& key, int Co, int Ci, int ksz, in
   need_dgrad = need_dgrad && !P.infer;
   c.need_dgrad = need_dgrad;
   c.transposed = false;
+  c.up2 = false;
   c.pb = -1;
   size_t n = (size_t)c.T * c.Cop * c.Cip;
   c.wf_hi = P.alloc(n * 2);
@@ -363,7 +366,7 @@ static void emit_norm_fwd(Plan& P, int ni, TRef x, TRef y) {
     // statistics -> coefficients -> normalise + ReLU in one launch (the coefficients are kept for the backward pass)
     LAUNCHED(cx, CAT_NORM, launch_gn_apply_fused(act_of(P, cx, x), act_of(P, cx, y), stats_ptr(P, cx, x), cx.params[n.pg],
                                                  cx.params[n.pb], n.C, n.G, n.S, 1e-5f,
-                                                 reinterpret_cast<float*>(cx.ws + n.coef), 0.f, cx.st));
+                                                 reinterpret_cast<float*>(cx.ws + n.coef), P.slope, cx.st));
     return OK;
   });
 }
@@ -417,7 +420,7 @@ static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
     WgradOp op;
     op.a = act_of(P, cx, a);
     op.dy = act_of(P, cx, dy);
-    op.ksz = c.ksz; op.stride = c.stride; op.Cip = c.Cip; op.Cop = c.Cop;
+    op.ksz = c.ksz; op.stride = c.stride; op.nopad = 0; op.Cip = c.Cip; op.Cop = c.Cop;
     op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
     LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
     return OK;
@@ -453,7 +456,7 @@ static void emit_dgrad(Plan& P, int ci, TRef dy, TRef out, int ni, TRef gn_x, TR
       op.gn_x = &gx;
       op.coef = reinterpret_cast<float*>(cx.ws + n.coef);
       op.coef_ld = n.Cld;
-      op.slope = 0.f;
+      op.slope = P.slope;
       op.bstats = reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats);
     }
     LAUNCHED(cx, cat, launch_igemm_conv(op, cx.st));
@@ -543,7 +546,9 @@ static TRef build_block_bwd(Plan& P, const BlockRec& r, TRef dOut) {
   return dX;
 }
 
-static int build(Plan& P) {
+static int finish_build(Plan& P);
+
+static int build_unet3d(Plan& P) {
   const b200unet_net_desc& d = P.d;
   const int L = d.n_levels, N = d.batch;
   B200_REQUIRE(L >= 2 && L <= 8, E_UNSUPPORTED, "plan: n_levels=%d unsupported (2..8)", L);
@@ -784,9 +789,15 @@ static int build(Plan& P) {
     return OK;
   });
   }  // !P.infer
-  // arenas that are bulk-zeroed
+  return finish_build(P);
+}
+
+// arenas that are bulk-zeroed + the weight (un)packing job tables
+static int finish_build(Plan& P) {
+  const b200unet_net_desc& d = P.d;
+  const int N = d.batch;
   B200_REQUIRE(P.params.size() <= 256, E_UNSUPPORTED, "plan: more than 256 parameter tensors");
-  P.drop_off = P.alloc(sizeof(float) * N * d.base_width);
+  P.drop_off = P.alloc(sizeof(float) * N * (d.base_width > 0 ? d.base_width : 8));
   P.stats_off = P.alloc(P.stats_bytes);
   P.bz_off = P.alloc(P.bz_bytes);
   for (size_t i = 0; i < P.convs.size(); ++i)
@@ -794,20 +805,306 @@ static int build(Plan& P) {
   for (const ConvLayer& c : P.convs) {
     PackJob j;
     j.pidx = c.pw; j.Co = c.Co; j.Ci = c.Ci; j.Cop = c.Cop; j.Cip = c.Cip; j.T = c.T;
-    j.mode = c.transposed ? 2 : 0; j.off_hi = (long long)c.wf_hi; j.off_lo = (long long)c.wf_lo;
+    j.mode = c.up2 ? 4 : c.transposed ? 2 : 0; j.off_hi = (long long)c.wf_hi; j.off_lo = (long long)c.wf_lo;
     P.pack_jobs.push_back(j);
     if (c.need_dgrad) {
-      j.mode = c.transposed ? 3 : 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo;
+      j.mode = (c.up2 || c.transposed) ? 3 : 1; j.off_hi = (long long)c.wd_hi; j.off_lo = (long long)c.wd_lo;
       P.pack_jobs.push_back(j);
     }
     if (P.infer) continue;
     PackJob u = j;
     u.mode = c.transposed ? 2 : 0; u.off_hi = (long long)(P.bz_off + c.dw); u.off_lo = 0;
+    if (c.up2) {   // accumulated with swapped roles as [T][pad(Co)][pad(Ci)] (see emit_wgrad_up2): reads back as [Ci][Co][T]
+      u.mode = 0; u.Co = c.Ci; u.Ci = c.Co; u.Cop = c.Cip; u.Cip = c.Cop;
+    }
     P.unpack_jobs.push_back(u);
   }
   P.jobs_off = P.alloc(sizeof(PackJob) * (P.pack_jobs.size() + P.unpack_jobs.size()));
   return OK;
 }
+
+
+// ================================================================================================ DynUNet (MONAI) blocks
+// What examples/brats2020/brats2020_config.json:2-107 and examples/sppin/sppin_config.json train.  MONAI's source is not
+// under /root/reference (third-party, absent from this image): the block semantics below restate its public definition
+// (monai/networks/nets/dynunet.py, monai/networks/blocks/dynunet_block.py) -- parity unpinned, see oracle/dynunet_oracle.py.
+//   UnetBasicBlock(in, out, k3, stride):  conv(bias-free, stride) -> InstanceNorm(affine) -> LeakyReLU(0.01)
+//                                         -> conv(s1) -> InstanceNorm -> LeakyReLU                  (post-activation order)
+//   UnetUpBlock(in, out):                 ConvTranspose3d(in -> out, kernel = stride = 2, bias-free) -> cat(up, skip) -> UnetBasicBlock(2 out -> out)
+//   UnetOutBlock:                         1x1x1 conv with bias
+//   DynUNet.forward: input_block, downsamples[...], bottleneck (strides 1, 2, 2, ...), upsamples mirrored, output_block.
+struct DynBlock {
+  TRef X;            // block input (activated output of the producer, or the concat buffer / packed network input)
+  TRef c1, a1, c2;   // conv1 output, its activated norm, conv2 output
+  TRef out;          // activated norm of c2 (may be the skip half of a concat buffer)
+  int n1, n2, k1, k2;
+  int stride;
+  bool first;
+};
+
+static void add_dyn_block_params(Plan& P, const std::string& pre, int cin, int cout) {
+  add_param(P, pre + ".conv1.conv.weight", {cout, cin, 3, 3, 3});
+  add_param(P, pre + ".conv2.conv.weight", {cout, cout, 3, 3, 3});
+  add_param(P, pre + ".norm1.weight", {cout});
+  add_param(P, pre + ".norm1.bias", {cout});
+  add_param(P, pre + ".norm2.weight", {cout});
+  add_param(P, pre + ".norm2.bias", {cout});
+}
+
+static int new_norm_keys(Plan& P, const std::string& prefix, int C, long long S) {
+  const int ni = new_norm(P, prefix, C, C, S);
+  P.norms[ni].G = C;   // instance norm: one group per channel
+  return ni;
+}
+
+static DynBlock build_dyn_block_fwd(Plan& P, const std::string& pre, TRef X, int cin_real, int C, int stride, TRef dest, bool first,
+                                    bool x_dead) {
+  const Buf& xb = P.bufs[X.buf];
+  const int N = xb.N, D = xb.D / stride, H = xb.H / stride, W = xb.W / stride;
+  const long long S = (long long)D * H * W;
+  DynBlock r;
+  r.X = X; r.stride = stride; r.first = first;
+  r.k1 = new_conv(P, pre + ".conv1.conv.weight", C, cin_real, 3, stride, !first);
+  r.k2 = new_conv(P, pre + ".conv2.conv.weight", C, C, 3, 1, true);
+  r.n1 = new_norm_keys(P, pre + ".norm1", C, S);
+  r.n2 = new_norm_keys(P, pre + ".norm2", C, S);
+  r.c1 = full(P, new_buf(P, N, D, H, W, C));
+  emit_conv_fwd(P, r.k1, X, -1, kNone, kNone, r.c1, true, false);
+  if (x_dead) release_if_whole(P, X);
+  r.a1 = full(P, new_buf(P, N, D, H, W, C));
+  emit_norm_fwd(P, r.n1, r.c1, r.a1);
+  r.c2 = full(P, new_buf(P, N, D, H, W, C));
+  emit_conv_fwd(P, r.k2, r.a1, -1, kNone, kNone, r.c2, true, false);
+  r.out = dest;
+  emit_norm_fwd(P, r.n2, r.c2, dest);
+  release_buf(P, r.c1.buf);
+  release_buf(P, r.a1.buf);
+  release_buf(P, r.c2.buf);
+  return r;
+}
+
+static void emit_act_bwd(Plan& P, int ni, TRef g1, TRef g2, TRef c, TRef dz) {
+  push_op(P.bwd, "act_bwd " + P.norms[ni].name + " " + shape_of(P, c), [&P, ni, g1, g2, c, dz](RunCtx& cx) -> int {
+    const NormLayer& n = P.norms[ni];
+    Act a2;
+    if (g2.valid()) a2 = act_of(P, cx, g2);
+    LAUNCHED(cx, CAT_NORM, launch_act_bwd(act_of(P, cx, g1), g2.valid() ? &a2 : nullptr, act_of(P, cx, c),
+                                          reinterpret_cast<float*>(cx.ws + n.coef), P.slope, act_of(P, cx, dz),
+                                          reinterpret_cast<double*>(cx.ws + P.bz_off + n.bstats), n.Cld, cx.st));
+    return OK;
+  });
+}
+
+// gradient of the block output arrives as g1 (+ g2); returns dX (kNone for the first block)
+static TRef build_dyn_block_bwd(Plan& P, const DynBlock& r, TRef g1, TRef g2) {
+  const Buf& cb = P.bufs[r.c1.buf];
+  const int N = cb.N, D = cb.D, H = cb.H, W = cb.W, C = r.c1.c;
+  TRef dz2 = full(P, new_buf(P, N, D, H, W, C));
+  emit_act_bwd(P, r.n2, g1, g2, r.c2, dz2);
+  TRef dc2 = full(P, new_buf(P, N, D, H, W, C));
+  emit_gn_bwd(P, r.n2, dz2, r.c2, kNone, dc2, false);
+  emit_wgrad(P, r.k2, r.a1, dc2);
+  TRef dz1 = full(P, new_buf(P, N, D, H, W, C));
+  emit_dgrad(P, r.k2, dc2, dz1, r.n1, r.c1, kNone, false, conv_macs(P, r.k2, dc2));   // mode 1: masked by act'(norm1(c1)) + statistics
+  TRef dc1 = full(P, new_buf(P, N, D, H, W, C));
+  emit_gn_bwd(P, r.n1, dz1, r.c1, kNone, dc1, false);
+  emit_wgrad(P, r.k1, r.X, dc1);
+  if (r.first) return kNone;
+  const Buf& xb = P.bufs[r.X.buf];
+  TRef dX = full(P, new_buf(P, N, xb.D, xb.H, xb.W, r.X.c));
+  emit_dgrad(P, r.k1, dc1, dX, -1, kNone, kNone, false, conv_macs(P, r.k1, dc1), /*cls_mode=*/r.stride == 2);
+  return dX;
+}
+
+static int build_dynunet(Plan& P) {
+  const b200unet_net_desc& d = P.d;
+  const int L = d.n_levels, N = d.batch;
+  B200_REQUIRE(L >= 2 && L <= 8, E_UNSUPPORTED, "plan: DynUNet with %d levels unsupported (2..8)", L);
+  B200_REQUIRE(d.n_features >= 1 && d.n_features <= 16, E_UNSUPPORTED, "plan: in_channels=%d unsupported", d.n_features);
+  B200_REQUIRE(d.n_outputs >= 1 && d.n_outputs <= 8, E_UNSUPPORTED, "plan: out_channels=%d unsupported", d.n_outputs);
+  P.slope = d.act_slope;
+  std::vector<int> F, Ds, Hs, Ws;
+  {
+    int D = d.depth, H = d.height, W = d.width;
+    for (int i = 0; i < L; ++i) {
+      B200_REQUIRE(d.filters[i] >= 8 && d.filters[i] % 8 == 0, E_UNSUPPORTED, "plan: filters[%d]=%d must be a positive multiple of 8", i,
+                   d.filters[i]);
+      F.push_back(d.filters[i]); Ds.push_back(D); Hs.push_back(H); Ws.push_back(W);
+      if (i + 1 < L)
+        B200_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D >= 2 && H >= 2 && W >= 2, E_UNSUPPORTED,
+                     "plan: level %d extent %dx%dx%d must be even (input %dx%dx%d not divisible by 2^%d)", i, D, H, W, d.depth,
+                     d.height, d.width, L - 1);
+      D /= 2; H /= 2; W /= 2;
+    }
+  }
+  // ---- parameter spec in MONAI's registration order: input_block, downsamples, bottleneck, upsamples, output_block
+  auto enc_name = [&](int i) -> std::string {
+    return i == 0 ? "input_block" : i == L - 1 ? "bottleneck" : "downsamples." + std::to_string(i - 1);
+  };
+  for (int i = 0; i < L; ++i) add_dyn_block_params(P, enc_name(i), i == 0 ? d.n_features : F[i - 1], F[i]);
+  for (int u = 0; u + 1 < L; ++u) {      // upsamples[u] maps level L-1-u -> L-2-u
+    const int lo = L - 1 - u, hi = L - 2 - u;
+    const std::string pre = "upsamples." + std::to_string(u);
+    add_param(P, pre + ".transp_conv.conv.weight", {F[lo], F[hi], 2, 2, 2});
+    add_dyn_block_params(P, pre + ".conv_block", 2 * F[hi], F[hi]);
+  }
+  add_param(P, "output_block.conv.conv.weight", {d.n_outputs, F[0], 1, 1, 1});
+  add_param(P, "output_block.conv.conv.bias", {d.n_outputs});
+
+  // ---- forward
+  const int Cp_in = round_up(d.n_features, 8);
+  const int b_in = new_buf(P, N, Ds[0], Hs[0], Ws[0], Cp_in);
+  push_op(P.fwd, "pack_weights+input_pack", [&P, b_in](RunCtx& cx) -> int {
+    B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.stats_off, 0, P.stats_bytes, cx.st));
+    if (P.jobs_uploaded_for != cx.ws) {
+      std::vector<PackJob> all(P.pack_jobs);
+      all.insert(all.end(), P.unpack_jobs.begin(), P.unpack_jobs.end());
+      B200_CHECK_CUDA(cudaMemcpyAsync(cx.ws + P.jobs_off, all.data(), sizeof(PackJob) * all.size(), cudaMemcpyHostToDevice, cx.st));
+      B200_CHECK_CUDA(cudaStreamSynchronize(cx.st));
+      P.jobs_uploaded_for = cx.ws;
+    }
+    PtrTable tbl;
+    memset(&tbl, 0, sizeof(tbl));
+    for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.params[i];
+    LAUNCHED(cx, CAT_PACK, launch_pack_all(tbl, reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off), (int)P.pack_jobs.size(), cx.ws,
+                                           P.split, cx.st));
+    TRef t = full(P, b_in);
+    LAUNCHED(cx, CAT_RESAMPLE, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), nullptr, P.bufs[b_in].C, cx.st));
+    return OK;
+  });
+  std::vector<int> cat(L, -1);
+  for (int i = 0; i + 1 < L; ++i) cat[i] = new_buf(P, N, Ds[i], Hs[i], Ws[i], 2 * F[i]);
+  std::vector<DynBlock> enc(L), dec(L);
+  std::vector<int> up(L, -1);
+  TRef X = full(P, b_in);
+  int cin_real = d.n_features;
+  for (int i = 0; i < L; ++i) {
+    TRef dest = (i + 1 < L) ? slice(full(P, cat[i]), F[i], F[i]) : full(P, new_buf(P, N, Ds[i], Hs[i], Ws[i], F[i]));
+    enc[i] = build_dyn_block_fwd(P, enc_name(i), X, cin_real, F[i], i == 0 ? 1 : 2, dest, i == 0, /*x_dead=*/i == 0);
+    X = dest;
+    cin_real = F[i];
+  }
+  for (int u = 0; u + 1 < L; ++u) {
+    const int lo = L - 1 - u, hi = L - 2 - u;
+    const std::string pre = "upsamples." + std::to_string(u);
+    up[hi] = new_conv(P, pre + ".transp_conv.conv.weight", F[hi], F[lo], 2, 2, true);
+    P.convs[up[hi]].up2 = true;
+    TRef U = slice(full(P, cat[hi]), 0, F[hi]);
+    {
+      const int ci = up[hi];
+      TRef Xin = X;
+      P.macs[CAT_CONV_FWD] += (double)N * Ds[lo] * Hs[lo] * Ws[lo] * F[lo] * F[hi] * 8;
+      push_op(P.fwd, "convT_k2s2 " + P.convs[ci].name + " " + shape_of(P, Xin) + "->" + shape_of(P, U), [&P, ci, Xin, U](RunCtx& cx) -> int {
+        const ConvLayer& c = P.convs[ci];
+        ConvOp op;
+        memset(&op, 0, sizeof(op));
+        op.nsrc = 1;
+        op.cls_mode = 2;
+        op.src[0].x = act_of(P, cx, Xin);
+        op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wf_hi);
+        op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wf_lo) : nullptr;
+        op.src[0].ksz = 2; op.src[0].nopad = 1; op.src[0].stride = 1; op.src[0].Cip = c.Cip;
+        op.Cop = c.Cop;
+        op.out = act_of(P, cx, U);
+        LAUNCHED(cx, CAT_CONV_FWD, launch_igemm_conv(op, cx.st));
+        return OK;
+      });
+    }
+    release_if_whole(P, X);
+    TRef dest = full(P, new_buf(P, N, Ds[hi], Hs[hi], Ws[hi], F[hi]));
+    dec[hi] = build_dyn_block_fwd(P, pre + ".conv_block", full(P, cat[hi]), 2 * F[hi], F[hi], 1, dest, false, /*x_dead=*/true);
+    X = dest;
+  }
+  const TRef Xfinal = X;
+  P.head_param = P.find_param("output_block.conv.conv.weight");
+  const int head_bias = P.find_param("output_block.conv.conv.bias");
+  push_op(P.fwd, "head_fwd", [&P, Xfinal, head_bias](RunCtx& cx) -> int {
+    LAUNCHED(cx, CAT_HEAD, launch_head_fwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, P.d.activation, cx.logits, cx.st,
+                                           cx.params[head_bias]));
+    return OK;
+  });
+  if (P.infer) return finish_build(P);
+
+  // ---- backward
+  B200_REQUIRE(d.activation == 0, E_UNSUPPORTED, "plan: activation inside the model is inference-only; train on logits");
+  push_op(P.bwd, "memset", [&P](RunCtx& cx) -> int {
+    B200_CHECK_CUDA(cudaMemsetAsync(cx.ws + P.bz_off, 0, P.bz_bytes, cx.st));
+    return OK;
+  });
+  TRef g;
+  {
+    const Buf xb = P.bufs[Xfinal.buf];
+    g = full(P, new_buf(P, N, xb.D, xb.H, xb.W, Xfinal.c));
+    TRef gg = g;
+    push_op(P.bwd, "head_bwd", [&P, Xfinal, gg, head_bias](RunCtx& cx) -> int {
+      LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits, act_of(P, cx, gg),
+                                             cx.grads[P.head_param], cx.st));
+      const Buf& b = P.bufs[Xfinal.buf];
+      LAUNCHED(cx, CAT_HEAD, launch_head_dbias(cx.dlogits, b.N, P.d.n_outputs, (long long)b.D * b.H * b.W, cx.grads[head_bias], cx.st));
+      return OK;
+    });
+  }
+  std::vector<TRef> dskip(L, kNone);
+  for (int hi = 0; hi + 1 < L; ++hi) {     // decoder, top (level 0) to bottom
+    const int lo = hi + 1;
+    TRef dCat = build_dyn_block_bwd(P, dec[hi], g, kNone);
+    dskip[hi] = slice(dCat, F[hi], F[hi]);
+    TRef dU = slice(dCat, 0, F[hi]);
+    const int ci = up[hi];
+    // input of the transposed convolution: the activated output of the stage below (or of the bottleneck)
+    const TRef Xlow = (lo == L - 1) ? enc[lo].out : dec[lo].out;
+    P.macs[CAT_CONV_WGRAD] += (double)N * Ds[lo] * Hs[lo] * Ws[lo] * F[lo] * F[hi] * 8;
+    push_op(P.bwd, "wgrad_up2 " + P.convs[ci].name, [&P, ci, Xlow, dU](RunCtx& cx) -> int {
+      // dW[ci][co][t] = sum_j X[j][ci] dU[2j + t][co]: the weight gradient of the kernel-2 stride-2 convolution that maps the
+      // FINE grid (dU, "input", channels co) to the COARSE grid (X, "output gradient", channels ci): accumulator [T][pad(Co)][pad(Ci)]
+      const ConvLayer& c = P.convs[ci];
+      WgradOp op;
+      op.a = act_of(P, cx, dU);
+      op.dy = act_of(P, cx, Xlow);
+      op.ksz = 2; op.stride = 2; op.nopad = 1; op.Cip = c.Cop; op.Cop = c.Cip;
+      op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
+      LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
+      return OK;
+    });
+    const Buf lb = P.bufs[Xlow.buf];
+    TRef gX = full(P, new_buf(P, N, lb.D, lb.H, lb.W, F[lo]));
+    P.macs[CAT_CONV_DGRAD] += (double)N * Ds[lo] * Hs[lo] * Ws[lo] * F[lo] * F[hi] * 8;
+    push_op(P.bwd, "dgrad_up2 " + P.convs[ci].name, [&P, ci, dU, gX](RunCtx& cx) -> int {
+      // dX[j][ci] = sum_t sum_co dU[2j + t][co] W[ci][co][t]: a kernel-2 stride-2 unpadded convolution of dU with the mode-3 pack
+      const ConvLayer& c = P.convs[ci];
+      ConvOp op;
+      memset(&op, 0, sizeof(op));
+      op.nsrc = 1;
+      op.src[0].x = act_of(P, cx, dU);
+      op.src[0].w_hi = reinterpret_cast<bf16*>(cx.ws + c.wd_hi);
+      op.src[0].w_lo = P.split ? reinterpret_cast<bf16*>(cx.ws + c.wd_lo) : nullptr;
+      op.src[0].ksz = 2; op.src[0].nopad = 1; op.src[0].stride = 2; op.src[0].Cip = c.Cop;
+      op.Cop = c.Cip;
+      op.out = act_of(P, cx, gX);
+      LAUNCHED(cx, CAT_CONV_DGRAD, launch_igemm_conv(op, cx.st));
+      return OK;
+    });
+    g = gX;
+  }
+  // g = gradient of the bottleneck output; encoder, bottom to top: skip gradient + gradient through the stride-2 conv below
+  TRef gdown = kNone;
+  for (int i = L - 1; i >= 0; --i) {
+    TRef g1 = (i == L - 1) ? g : dskip[i];
+    TRef g2 = (i == L - 1) ? kNone : gdown;
+    gdown = build_dyn_block_bwd(P, enc[i], g1, g2);
+  }
+  push_op(P.bwd, "unpack_wgrads", [&P](RunCtx& cx) -> int {
+    PtrTable tbl;
+    memset(&tbl, 0, sizeof(tbl));
+    for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.grads[i];
+    const PackJob* jobs = reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off) + P.pack_jobs.size();
+    LAUNCHED(cx, CAT_PACK, launch_unpack_all(tbl, jobs, (int)P.unpack_jobs.size(), cx.ws, cx.st));
+    return OK;
+  });
+  return finish_build(P);
+}
+
+static int build(Plan& P) { return P.d.arch == 1 ? build_dynunet(P) : build_unet3d(P); }
 
 }  // namespace b200
 

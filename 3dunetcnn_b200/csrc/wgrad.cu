@@ -30,7 +30,7 @@ struct WgradArgs {
   int N, Do, Ho, Wo;
   int Ci, Co, Cip, Cop;
   int tw, th, td, tiles_w, tiles_h, tiles_d;
-  int ksz, stride, ntaps;
+  int ksz, stride, ntaps, pad;
   int nci;        // ci chunks per tap
   int units;      // ntaps * nci
   int qtiles;     // M-tiles in total
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int pad = p.ksz >> 1;
+  const int pad = p.pad;
 
   if (warp == 0) {
     {
@@ -238,6 +238,7 @@ static int launch_wg(const WgradMaps& maps, const WgradArgs& a, dim3 grid, cudaS
 
 int launch_wgrad(const WgradOp& op, cudaStream_t st) {
   static const bool no_halo = getenv("B200UNET_NO_HALO_WGRAD") != nullptr;
+  if (wgrad_1x1_narrow_eligible(op)) return launch_wgrad_1x1_narrow(op, st);
   if (!no_halo && wgrad_halo_eligible(op)) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -249,13 +250,14 @@ int launch_wgrad(const WgradOp& op, cudaStream_t st) {
 int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st) {
   const Act& A = op.a;
   const Act& Y = op.dy;
-  B200_REQUIRE(op.ksz == 1 || op.ksz == 3, E_UNSUPPORTED, "wgrad: kernel_size=%d unsupported", op.ksz);
+  B200_REQUIRE(op.ksz == 1 || op.ksz == 3 || (op.ksz == 2 && op.nopad && op.stride == 2), E_UNSUPPORTED,
+               "wgrad: kernel_size=%d unsupported", op.ksz);
   B200_REQUIRE(op.stride == 1 || op.stride == 2, E_UNSUPPORTED, "wgrad: stride=%d unsupported", op.stride);
   B200_REQUIRE(A.C % 8 == 0 && Y.C % 8 == 0 && A.ld % 8 == 0 && Y.ld % 8 == 0, E_UNSUPPORTED,
                "wgrad: channels must be multiples of 8 (Ci=%d Co=%d)", A.C, Y.C);
   B200_REQUIRE(op.Cop % 4 == 0 && op.Cop >= Y.C && op.Cip >= A.C, E_INVALID, "wgrad: bad accumulator pitch");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(op.dw) & 15) == 0, E_INVALID, "wgrad: dw not 16B aligned");
-  const int pad = op.ksz / 2;
+  const int pad = op.nopad ? 0 : op.ksz / 2;
   B200_REQUIRE((A.D + 2 * pad - op.ksz) / op.stride + 1 == Y.D && (A.H + 2 * pad - op.ksz) / op.stride + 1 == Y.H &&
                    (A.W + 2 * pad - op.ksz) / op.stride + 1 == Y.W && A.N == Y.N,
                E_INVALID, "wgrad: shape mismatch");
@@ -270,7 +272,7 @@ int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st) {
   a.Ci = A.C; a.Co = Y.C; a.Cip = op.Cip; a.Cop = op.Cop;
   pick_tile_w(Y.W, Y.H, Y.D, a.tw, a.th, a.td);
   a.tiles_w = ceil_div(Y.W, a.tw); a.tiles_h = ceil_div(Y.H, a.th); a.tiles_d = ceil_div(Y.D, a.td);
-  a.ksz = op.ksz; a.stride = op.stride; a.ntaps = op.ksz * op.ksz * op.ksz;
+  a.ksz = op.ksz; a.stride = op.stride; a.ntaps = op.ksz * op.ksz * op.ksz; a.pad = pad;
   const int CB = A.C > 32 ? 64 : A.C > 16 ? 32 : 16;
   const int BN = Y.C > 64 ? 128 : Y.C > 32 ? 64 : Y.C > 16 ? 32 : 16;
   const int CBN = BN < 64 ? BN : 64;

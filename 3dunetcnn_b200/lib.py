@@ -39,7 +39,8 @@ class NetDesc(C.Structure):
                 ("feature_dilation", C.c_int32), ("norm_groups", C.c_int32),
                 ("use_transposed_convolutions", C.c_int32), ("activation", C.c_int32),
                 ("split_precision", C.c_int32), ("batch", C.c_int32), ("depth", C.c_int32), ("height", C.c_int32),
-                ("width", C.c_int32), ("inference_only", C.c_int32)]
+                ("width", C.c_int32), ("arch", C.c_int32), ("filters", C.c_int32 * 8), ("act_slope", C.c_float),
+                ("inference_only", C.c_int32)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -92,6 +93,8 @@ _SIGS = {
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200unet_dice_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200unet_act_bwd": (C.c_int, [C.POINTER(Tensor5), C.POINTER(Tensor5), C.POINTER(Tensor5), C.c_void_p, C.c_float,
+                                   C.POINTER(Tensor5), C.c_void_p, C.c_int, C.c_void_p]),
     "b200unet_tiles_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "b200unet_tiles_scatter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -216,14 +219,14 @@ def pack_weights(w: torch.Tensor, mode: int = 0, split: bool = False, cop: Optio
                  cip: Optional[int] = None):
     """torch conv weight -> packed bf16 GEMM operand(s).  Returns (hi, lo|None, cop, cip, taps)."""
     w = w.contiguous().float()
-    if mode == 2:
+    if mode >= 2:                                   # ConvTranspose3d weight [Ci][Co][k^3]
         ci, co = w.shape[0], w.shape[1]
     else:
         co, ci = w.shape[0], w.shape[1]
     taps = int(w.shape[2] * w.shape[3] * w.shape[4])
     cop = (co + 7) // 8 * 8 if cop is None else cop
     cip = (ci + 7) // 8 * 8 if cip is None else cip
-    shape = (taps, cip, cop) if mode == 1 else (taps, cop, cip)
+    shape = (taps, cip, cop) if mode in (1, 3) else (taps, cop, cip)
     hi = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
     lo = torch.empty(shape, dtype=torch.bfloat16, device=w.device) if split else None
     check(load_library().b200unet_pack_weights(w.data_ptr(), co, ci, cop, cip, taps, mode, hi.data_ptr(),

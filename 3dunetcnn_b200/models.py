@@ -153,52 +153,16 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
-class UNet3D(nn.Module):
-    """Drop-in for the reference ``UNet3D`` (same ctor kwargs, same state_dict), B200-native arithmetic.
+class _PlanModel(nn.Module):
+    """Shared machinery of the plan-backed models: canonical fp32 parameters under the reference's state-dict keys, a
+    cache of whole-network plans keyed by input shape, gradient placement.  Subclasses provide ``_param_spec_cpu`` (ordered
+    (key, shape) list), ``_net_desc`` (the library's network descriptor) and ``_init_tensor``."""
 
-    Extra kwarg ``precision``: ``"bf16"`` (default; single-pass bf16 tensor-core operands, fp32 accumulate) or
-    ``"split"`` (hi/lo bf16 operand split, three MMAs per product: the parity mode that meets 1e-3 vs fp32).
-    ``B200UNET_PRECISION`` overrides the default.
-    """
-
-    def __init__(self, input_shape=None, n_features=1, base_width=32, encoder_blocks=None, decoder_blocks=None,
-                 feature_dilation=2, downsampling_stride=2, interpolation_mode="trilinear", encoder_class=None,
-                 decoder_class=None, n_outputs=1, layer_widths=None, decoder_mirrors_encoder=False, activation=None,
-                 use_transposed_convolutions=False, kernel_size=3, precision: Optional[str] = None,
-                 dropout: float = 0.2, norm_groups: int = 8):
-        super().__init__()
-        if downsampling_stride != 2:
-            raise NotImplementedError("B200 UNet3D: downsampling_stride=%r (only 2 is implemented)" % (downsampling_stride,))
-        if interpolation_mode != "trilinear":
-            raise NotImplementedError("B200 UNet3D: interpolation_mode=%r (only 'trilinear')" % (interpolation_mode,))
-        if kernel_size != 3:
-            raise NotImplementedError("B200 UNet3D: kernel_size=%r (only 3)" % (kernel_size,))
-        if layer_widths is not None:
-            raise NotImplementedError("B200 UNet3D: layer_widths is not supported (the reference's UNet3D also breaks on it)")
-        if encoder_class is not None or decoder_class is not None:
-            raise NotImplementedError("B200 UNet3D: custom encoder/decoder classes are not supported")
-        if activation not in _ACT:
-            raise ValueError("activation must be None, 'sigmoid' or 'softmax'")
-        if encoder_blocks is None:
-            encoder_blocks = [1, 2, 2, 4]                       # variational.py:44-45
-        if decoder_mirrors_encoder:
-            decoder_blocks = list(encoder_blocks)               # variational.py:71-74
-        elif decoder_blocks is None:
-            decoder_blocks = [1] * len(encoder_blocks)          # variational.py:75-76
-        if len(decoder_blocks) != len(encoder_blocks):
-            raise ValueError("decoder_blocks and encoder_blocks must have the same length")
+    def _setup(self, precision: Optional[str]) -> None:
         precision = precision or os.environ.get("B200UNET_PRECISION", "bf16")
         if precision not in ("bf16", "split"):
             raise ValueError("precision must be 'bf16' or 'split'")
         self.precision = precision
-        self.input_shape = input_shape
-        self.n_features, self.n_outputs, self.base_width = int(n_features), int(n_outputs), int(base_width)
-        self.encoder_blocks, self.decoder_blocks = [int(b) for b in encoder_blocks], [int(b) for b in decoder_blocks]
-        self.feature_dilation = int(feature_dilation)
-        self.use_transposed_convolutions = bool(use_transposed_convolutions)
-        self.activation_name = activation
-        self.dropout_p = float(dropout)                          # myronenko.py:85 (hard-wired 0.2 in the reference)
-        self.norm_groups = int(norm_groups)
         self._plans: Dict[Tuple, _Plan] = {}
         self.launches_last_forward = 0
         self.launches_last_backward = 0
@@ -206,96 +170,20 @@ class UNet3D(nn.Module):
         self._flat_grads = False
         self._grad_bucket: Optional[torch.Tensor] = None
         self._grad_views = None
-
-        # parameters under the reference's keys, default torch init
         self._keys = []
         spec = self._param_spec_cpu()
         shapes = dict(spec)
         for key, shape in spec:
             t = torch.empty(shape, dtype=torch.float32)
-            if key.endswith("norm1.weight"):
-                nn.init.ones_(t)
-            elif key.endswith("norm1.bias"):
-                nn.init.zeros_(t)
-            else:
-                wshape = shapes[key[:-5] + ".weight"] if key.endswith(".bias") else shape
-                fan_in = wshape[1] * wshape[2] * wshape[3] * wshape[4]   # torch default: weight.size(1) * k^3
-                bound = 1.0 / math.sqrt(fan_in)
-                nn.init.uniform_(t, -bound, bound)
+            self._init_tensor(key, t, shapes)
             _register(self, key, nn.Parameter(t))
             self._keys.append(key)
-
-    # ------------------------------------------------------------------ spec (pure python twin of plan.cu's)
-    def _dec_widths(self, depth: int) -> Tuple[int, int]:
-        n = len(self.encoder_blocks)
-        if depth > 0:
-            out_w = self.base_width * self.feature_dilation ** (depth - 1)
-            in_w = out_w * self.feature_dilation
-        else:
-            out_w = in_w = self.base_width
-        if depth != n - 1:
-            in_w *= 2
-        return in_w, out_w
-
-    def _param_spec_cpu(self):
-        spec = []
-
-        def block(prefix, cin, cout):
-            spec.append((prefix + ".conv1.norm1.weight", (cin,)))
-            spec.append((prefix + ".conv1.norm1.bias", (cin,)))
-            spec.append((prefix + ".conv1.conv.weight", (cout, cin, 3, 3, 3)))
-            spec.append((prefix + ".conv2.norm1.weight", (cout,)))
-            spec.append((prefix + ".conv2.norm1.bias", (cout,)))
-            spec.append((prefix + ".conv2.conv.weight", (cout, cout, 3, 3, 3)))
-            if cin != cout:
-                spec.append((prefix + ".sample.weight", (cout, cin, 1, 1, 1)))
-
-        n = len(self.encoder_blocks)
-        widths = [self.base_width * self.feature_dilation ** i for i in range(n)]
-        cin = self.n_features
-        for li, nb in enumerate(self.encoder_blocks):
-            for b in range(nb):
-                block("encoder.layers.%d.blocks.%d" % (li, b), cin if b == 0 else widths[li], widths[li])
-            cin = widths[li]
-        for li in range(n - 1):
-            spec.append(("encoder.downsampling_convolutions.%d.weight" % li, (widths[li], widths[li], 3, 3, 3)))
-        for i, nb in enumerate(self.decoder_blocks):
-            depth = n - 1 - i
-            in_w, out_w = self._dec_widths(depth)
-            planes = in_w if depth != 0 else out_w
-            for b in range(nb):
-                block("decoder.layers.%d.blocks.%d" % (i, b), in_w if b == 0 else planes, planes)
-        for i in range(n - 1):
-            in_w, out_w = self._dec_widths(n - 1 - i)
-            if self.use_transposed_convolutions:
-                spec.append(("decoder.upsampling_blocks.%d.weight" % i, (in_w, out_w, 3, 3, 3)))
-                spec.append(("decoder.upsampling_blocks.%d.bias" % i, (out_w,)))
-            else:
-                spec.append(("decoder.pre_upsampling_blocks.%d.weight" % i, (out_w, in_w, 1, 1, 1)))
-        spec.append(("final_convolution.weight", (self.n_outputs, self.base_width, 1, 1, 1)))
-        return spec
 
     def ordered_parameters(self):
         sd = dict(self.named_parameters())
         return [sd[k] for k in self._keys]
 
     # ------------------------------------------------------------------ plan cache
-    def _net_desc(self, n, d, h, w) -> _lib.NetDesc:
-        nd = _lib.NetDesc()
-        nd.n_features, nd.n_outputs, nd.base_width = self.n_features, self.n_outputs, self.base_width
-        nd.n_levels = len(self.encoder_blocks)
-        for i, b in enumerate(self.encoder_blocks):
-            nd.encoder_blocks[i] = b
-        for i, b in enumerate(self.decoder_blocks):
-            nd.decoder_blocks[i] = b
-        nd.feature_dilation = self.feature_dilation
-        nd.norm_groups = self.norm_groups
-        nd.use_transposed_convolutions = int(self.use_transposed_convolutions)
-        nd.activation = _ACT[self.activation_name]
-        nd.split_precision = int(self.precision == "split")
-        nd.batch, nd.depth, nd.height, nd.width = n, d, h, w
-        return nd
-
     def _plan_for(self, x: torch.Tensor, inference_only: bool = False) -> _Plan:
         n, _, d, h, w = x.shape
         key = (n, d, h, w, self.precision, x.device.index, bool(inference_only))
@@ -355,25 +243,156 @@ class UNet3D(nn.Module):
 
     _overwrite_grads = False   # set by train.GraphedTrainStep while it owns the step
 
+    def _check_input(self, x: torch.Tensor, n_in: int) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor) or x.dim() != 5:
+            raise ValueError("%s expects a 5-D tensor [N, C, D, H, W]" % type(self).__name__)
+        if not x.is_cuda:
+            raise RuntimeError("B200 %s runs only on CUDA tensors (no CPU fallback); got device %s" % (type(self).__name__, x.device))
+        if x.shape[1] != n_in:
+            raise ValueError("expected %d input channels, got %d" % (n_in, x.shape[1]))
+        if x.requires_grad:
+            raise NotImplementedError("B200 %s does not produce input gradients" % type(self).__name__)
+        xp = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x   # MetaTensor -> plain view
+        xp = xp.detach().contiguous().float()
+        params = self.ordered_parameters()
+        if params[0].device != xp.device:
+            raise RuntimeError("model parameters are on %s but the input is on %s" % (params[0].device, xp.device))
+        return xp
+
+
+class UNet3D(_PlanModel):
+    """Drop-in for the reference ``UNet3D`` (same ctor kwargs, same state_dict), B200-native arithmetic.
+
+    Extra kwarg ``precision``: ``"bf16"`` (default; single-pass bf16 tensor-core operands, fp32 accumulate) or
+    ``"split"`` (hi/lo bf16 operand split, three MMAs per product: the parity mode that meets 1e-3 vs fp32).
+    ``B200UNET_PRECISION`` overrides the default.
+    """
+
+    def __init__(self, input_shape=None, n_features=1, base_width=32, encoder_blocks=None, decoder_blocks=None,
+                 feature_dilation=2, downsampling_stride=2, interpolation_mode="trilinear", encoder_class=None,
+                 decoder_class=None, n_outputs=1, layer_widths=None, decoder_mirrors_encoder=False, activation=None,
+                 use_transposed_convolutions=False, kernel_size=3, precision: Optional[str] = None,
+                 dropout: float = 0.2, norm_groups: int = 8):
+        super().__init__()
+        if downsampling_stride != 2:
+            raise NotImplementedError("B200 UNet3D: downsampling_stride=%r (only 2 is implemented)" % (downsampling_stride,))
+        if interpolation_mode != "trilinear":
+            raise NotImplementedError("B200 UNet3D: interpolation_mode=%r (only 'trilinear')" % (interpolation_mode,))
+        if kernel_size != 3:
+            raise NotImplementedError("B200 UNet3D: kernel_size=%r (only 3)" % (kernel_size,))
+        if layer_widths is not None:
+            raise NotImplementedError("B200 UNet3D: layer_widths is not supported (the reference's UNet3D also breaks on it)")
+        if encoder_class is not None or decoder_class is not None:
+            raise NotImplementedError("B200 UNet3D: custom encoder/decoder classes are not supported")
+        if activation not in _ACT:
+            raise ValueError("activation must be None, 'sigmoid' or 'softmax'")
+        if encoder_blocks is None:
+            encoder_blocks = [1, 2, 2, 4]                       # variational.py:44-45
+        if decoder_mirrors_encoder:
+            decoder_blocks = list(encoder_blocks)               # variational.py:71-74
+        elif decoder_blocks is None:
+            decoder_blocks = [1] * len(encoder_blocks)          # variational.py:75-76
+        if len(decoder_blocks) != len(encoder_blocks):
+            raise ValueError("decoder_blocks and encoder_blocks must have the same length")
+        self.input_shape = input_shape
+        self.n_features, self.n_outputs, self.base_width = int(n_features), int(n_outputs), int(base_width)
+        self.encoder_blocks, self.decoder_blocks = [int(b) for b in encoder_blocks], [int(b) for b in decoder_blocks]
+        self.feature_dilation = int(feature_dilation)
+        self.use_transposed_convolutions = bool(use_transposed_convolutions)
+        self.activation_name = activation
+        self.dropout_p = float(dropout)                          # myronenko.py:85 (hard-wired 0.2 in the reference)
+        self.norm_groups = int(norm_groups)
+        self.dropout_width = self.base_width
+        self._setup(precision)                                   # parameters under the reference's keys (SURVEY appendix B)
+
+    @staticmethod
+    def _init_tensor(key, t, shapes):
+        """default torch init of the reference's modules (Conv3d: U(+-1/sqrt(fan_in)); GroupNorm: 1 / 0)"""
+        if key.endswith("norm1.weight"):
+            nn.init.ones_(t)
+        elif key.endswith("norm1.bias"):
+            nn.init.zeros_(t)
+        else:
+            wshape = shapes[key[:-5] + ".weight"] if key.endswith(".bias") else tuple(t.shape)
+            fan_in = wshape[1] * wshape[2] * wshape[3] * wshape[4]   # torch default: weight.size(1) * k^3
+            bound = 1.0 / math.sqrt(fan_in)
+            nn.init.uniform_(t, -bound, bound)
+
+    # ------------------------------------------------------------------ spec (pure python twin of plan.cu's)
+    def _dec_widths(self, depth: int) -> Tuple[int, int]:
+        n = len(self.encoder_blocks)
+        if depth > 0:
+            out_w = self.base_width * self.feature_dilation ** (depth - 1)
+            in_w = out_w * self.feature_dilation
+        else:
+            out_w = in_w = self.base_width
+        if depth != n - 1:
+            in_w *= 2
+        return in_w, out_w
+
+    def _param_spec_cpu(self):
+        spec = []
+
+        def block(prefix, cin, cout):
+            spec.append((prefix + ".conv1.norm1.weight", (cin,)))
+            spec.append((prefix + ".conv1.norm1.bias", (cin,)))
+            spec.append((prefix + ".conv1.conv.weight", (cout, cin, 3, 3, 3)))
+            spec.append((prefix + ".conv2.norm1.weight", (cout,)))
+            spec.append((prefix + ".conv2.norm1.bias", (cout,)))
+            spec.append((prefix + ".conv2.conv.weight", (cout, cout, 3, 3, 3)))
+            if cin != cout:
+                spec.append((prefix + ".sample.weight", (cout, cin, 1, 1, 1)))
+
+        n = len(self.encoder_blocks)
+        widths = [self.base_width * self.feature_dilation ** i for i in range(n)]
+        cin = self.n_features
+        for li, nb in enumerate(self.encoder_blocks):
+            for b in range(nb):
+                block("encoder.layers.%d.blocks.%d" % (li, b), cin if b == 0 else widths[li], widths[li])
+            cin = widths[li]
+        for li in range(n - 1):
+            spec.append(("encoder.downsampling_convolutions.%d.weight" % li, (widths[li], widths[li], 3, 3, 3)))
+        for i, nb in enumerate(self.decoder_blocks):
+            depth = n - 1 - i
+            in_w, out_w = self._dec_widths(depth)
+            planes = in_w if depth != 0 else out_w
+            for b in range(nb):
+                block("decoder.layers.%d.blocks.%d" % (i, b), in_w if b == 0 else planes, planes)
+        for i in range(n - 1):
+            in_w, out_w = self._dec_widths(n - 1 - i)
+            if self.use_transposed_convolutions:
+                spec.append(("decoder.upsampling_blocks.%d.weight" % i, (in_w, out_w, 3, 3, 3)))
+                spec.append(("decoder.upsampling_blocks.%d.bias" % i, (out_w,)))
+            else:
+                spec.append(("decoder.pre_upsampling_blocks.%d.weight" % i, (out_w, in_w, 1, 1, 1)))
+        spec.append(("final_convolution.weight", (self.n_outputs, self.base_width, 1, 1, 1)))
+        return spec
+
+    # ------------------------------------------------------------------ library descriptor
+    def _net_desc(self, n, d, h, w) -> _lib.NetDesc:
+        nd = _lib.NetDesc()
+        nd.n_features, nd.n_outputs, nd.base_width = self.n_features, self.n_outputs, self.base_width
+        nd.n_levels = len(self.encoder_blocks)
+        for i, b in enumerate(self.encoder_blocks):
+            nd.encoder_blocks[i] = b
+        for i, b in enumerate(self.decoder_blocks):
+            nd.decoder_blocks[i] = b
+        nd.feature_dilation = self.feature_dilation
+        nd.norm_groups = self.norm_groups
+        nd.use_transposed_convolutions = int(self.use_transposed_convolutions)
+        nd.activation = _ACT[self.activation_name]
+        nd.split_precision = int(self.precision == "split")
+        nd.batch, nd.depth, nd.height, nd.width = n, d, h, w
+        return nd
+
     def set_dropout_scale(self, scale: Optional[torch.Tensor]) -> None:
         """Testing hook: force the (N, C0) Dropout3d channel scale used by the next training forwards."""
         self._forced_dropout_scale = scale
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if not isinstance(x, torch.Tensor) or x.dim() != 5:
-            raise ValueError("UNet3D expects a 5-D tensor [N, C, D, H, W]")
-        if not x.is_cuda:
-            raise RuntimeError("B200 UNet3D runs only on CUDA tensors (no CPU fallback); got device %s" % x.device)
-        if x.shape[1] != self.n_features:
-            raise ValueError("expected %d input channels, got %d" % (self.n_features, x.shape[1]))
-        if x.requires_grad:
-            raise NotImplementedError("B200 UNet3D does not produce input gradients")
-        xp = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x   # MetaTensor -> plain view
-        xp = xp.detach().contiguous().float()
+        xp = self._check_input(x, self.n_features)
         params = self.ordered_parameters()
-        if params[0].device != xp.device:
-            raise RuntimeError("model parameters are on %s but the input is on %s" % (params[0].device, xp.device))
         drop = None
         if self.training and self.dropout_p > 0:
             if self._forced_dropout_scale is not None:
@@ -403,8 +422,118 @@ class AutoImplantUNet(UNet3D):
         return super().forward(x)
 
 
+class DynUNet(_PlanModel):
+    """Drop-in for ``monai.networks.nets.DynUNet`` as the reference's example configs instantiate it
+    (examples/brats2020/brats2020_config.json:2-107, examples/sppin/sppin_config.json: ``getattr(unet3d.models.pytorch,
+    "DynUNet")(**kwargs)`` through the ``from monai.networks.nets import *`` in unet3d/models/pytorch/__init__.py:1).
+
+    MONAI's kwarg names; implemented: ``spatial_dims=3``, ``kernel_size`` all 3, ``strides`` [1, 2, 2, ...],
+    ``upsample_kernel_size`` all 2 (transposed convolution with kernel = stride), instance norm (affine), LeakyReLU,
+    ``res_block=False``, ``deep_supervision=False``, ``trans_bias=False``, ``dropout=None``; anything else raises.
+    State-dict keys follow MONAI's module names (input_block / downsamples.N / bottleneck / upsamples.N / output_block);
+    MONAI additionally exposes the same tensors a second time under ``skip_layers.*`` -- load such a checkpoint with
+    ``strict=False`` (parity with MONAI itself is unpinned: it is absent from this image)."""
+
+    def __init__(self, spatial_dims=3, in_channels=1, out_channels=1, kernel_size=None, strides=None, upsample_kernel_size=None,
+                 filters=None, dropout=None, norm_name=("INSTANCE", {"affine": True}),
+                 act_name=("leakyrelu", {"inplace": True, "negative_slope": 0.01}), deep_supervision=False, deep_supr_num=1,
+                 res_block=False, trans_bias=False, precision: Optional[str] = None):
+        super().__init__()
+
+        def triple(v):
+            return [int(v)] * 3 if isinstance(v, int) else [int(e) for e in v]
+        if spatial_dims != 3:
+            raise NotImplementedError("B200 DynUNet: spatial_dims=%r (only 3)" % (spatial_dims,))
+        if strides is None or kernel_size is None:
+            raise ValueError("DynUNet needs kernel_size and strides")
+        strides = [triple(v) for v in strides]
+        kernel_size = [triple(v) for v in kernel_size]
+        if upsample_kernel_size is None:
+            upsample_kernel_size = strides[1:]
+        upsample_kernel_size = [triple(v) for v in upsample_kernel_size]
+        if len(kernel_size) != len(strides) or len(upsample_kernel_size) != len(strides) - 1:
+            raise ValueError("length of kernel_size and strides should be the same, upsample_kernel_size one shorter")
+        if any(k != [3, 3, 3] for k in kernel_size):
+            raise NotImplementedError("B200 DynUNet: kernel_size must be 3 at every level")
+        if strides[0] != [1, 1, 1] or any(v != [2, 2, 2] for v in strides[1:]):
+            raise NotImplementedError("B200 DynUNet: strides must be [1, 2, 2, ...]")
+        if any(v != [2, 2, 2] for v in upsample_kernel_size):
+            raise NotImplementedError("B200 DynUNet: upsample_kernel_size must be 2 (= stride) at every level")
+        norm = (norm_name if isinstance(norm_name, str) else norm_name[0]).lower()
+        norm_kw = {} if isinstance(norm_name, str) else dict(norm_name[1])
+        if norm != "instance" or not norm_kw.get("affine", False):
+            raise NotImplementedError("B200 DynUNet: norm_name must be ('INSTANCE', {'affine': True})")
+        act = (act_name if isinstance(act_name, str) else act_name[0]).lower()
+        act_kw = {} if isinstance(act_name, str) else dict(act_name[1])
+        if act not in ("leakyrelu", "relu"):
+            raise NotImplementedError("B200 DynUNet: act_name %r (only leakyrelu / relu)" % (act_name,))
+        if deep_supervision or res_block or trans_bias or dropout is not None:
+            raise NotImplementedError("B200 DynUNet: deep_supervision / res_block / trans_bias / dropout are not implemented")
+        if filters is None:
+            filters = [min(2 ** (5 + i), 320) for i in range(len(strides))]      # MONAI's default for spatial_dims = 3
+        filters = [int(f) for f in filters][:len(strides)]
+        if len(filters) < len(strides):
+            raise ValueError("length of filters should be no less than the length of strides")
+        if not 2 <= len(filters) <= 8:
+            raise NotImplementedError("B200 DynUNet: 2..8 levels")
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.n_features, self.n_outputs = self.in_channels, self.out_channels
+        self.filters = filters
+        self.act_slope = float(act_kw.get("negative_slope", 0.01)) if act == "leakyrelu" else 0.0
+        self._setup(precision)
+
+    def _param_spec_cpu(self):
+        spec = []
+        L = len(self.filters)
+        F = self.filters
+
+        def block(prefix, cin, cout):
+            spec.append((prefix + ".conv1.conv.weight", (cout, cin, 3, 3, 3)))
+            spec.append((prefix + ".conv2.conv.weight", (cout, cout, 3, 3, 3)))
+            for n in ("norm1", "norm2"):
+                spec.append((prefix + "." + n + ".weight", (cout,)))
+                spec.append((prefix + "." + n + ".bias", (cout,)))
+        for i in range(L):
+            name = "input_block" if i == 0 else "bottleneck" if i == L - 1 else "downsamples.%d" % (i - 1)
+            block(name, self.in_channels if i == 0 else F[i - 1], F[i])
+        for u in range(L - 1):
+            lo, hi = L - 1 - u, L - 2 - u
+            spec.append(("upsamples.%d.transp_conv.conv.weight" % u, (F[lo], F[hi], 2, 2, 2)))
+            block("upsamples.%d.conv_block" % u, 2 * F[hi], F[hi])
+        spec.append(("output_block.conv.conv.weight", (self.out_channels, F[0], 1, 1, 1)))
+        spec.append(("output_block.conv.conv.bias", (self.out_channels,)))
+        return spec
+
+    def _init_tensor(self, key, t, shapes):
+        """MONAI DynUNet.initialize_weights: kaiming_normal_(a=0.01) on conv / transposed-conv weights, zero biases;
+        InstanceNorm affine 1 / 0."""
+        if ".norm" in key:
+            (nn.init.ones_ if key.endswith("weight") else nn.init.zeros_)(t)
+        elif key.endswith(".bias"):
+            nn.init.zeros_(t)
+        else:
+            nn.init.kaiming_normal_(t, a=0.01)
+
+    def _net_desc(self, n, d, h, w) -> _lib.NetDesc:
+        nd = _lib.NetDesc()
+        nd.arch = 1
+        nd.n_features, nd.n_outputs = self.in_channels, self.out_channels
+        nd.n_levels = len(self.filters)
+        for i, f in enumerate(self.filters):
+            nd.filters[i] = f
+        nd.act_slope = self.act_slope
+        nd.activation = 0
+        nd.split_precision = int(self.precision == "split")
+        nd.batch, nd.depth, nd.height, nd.width = n, d, h, w
+        return nd
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        xp = self._check_input(x, self.in_channels)
+        return _UNetFunction.apply(self, xp, None, *self.ordered_parameters())
+
+
 _MODELS = {"UNet3D": UNet3D, "AutocastUNet": AutocastUNet, "AutoImplantUNet": AutoImplantUNet,
-           "B200UNet3D": UNet3D}
+           "B200UNet3D": UNet3D, "DynUNet": DynUNet}
 
 
 def fetch_model_by_name(model_name, *args, **kwargs):

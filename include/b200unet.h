@@ -48,7 +48,9 @@ int b200unet_ndhwc_to_ncdhw(const b200unet_tensor* in, int c_real, float* y, voi
 
 /* ---- weight packing.  torch Conv3d weight [Co][Ci][k^3] fp32 (resnet.py:12-22) -> bf16 GEMM operand.
  *   mode 0: [T][Cop][Cip]  forward;  mode 1: [T][Cip][Cop] taps flipped (data gradient);
- *   mode 2: ConvTranspose3d weight [Ci][Co][k^3] (decoder.py:101-102) -> [T][Cop][Cip] flipped. */
+ *   mode 2: ConvTranspose3d weight [Ci][Co][k^3] (decoder.py:101-102) -> [T][Cop][Cip] flipped;
+ *   mode 3: the same weight -> [T][Cip][Cop] unflipped (its data gradient);  mode 4: -> [T][Cop][Cip] unflipped
+ *   (forward of a kernel = stride transposed convolution, MONAI UnetUpBlock). */
 int b200unet_pack_weights(const float* w, int co, int ci, int cop, int cip, int taps, int mode, void* hi, void* lo,
                           void* stream);
 /* fp32 [T][Cip][Cop] accumulator -> torch gradient layout (mode 0: [Co][Ci][T]; mode 2: [Ci][Co][T] flipped) */
@@ -95,6 +97,11 @@ int b200unet_gn_bwd_finalize(const double* bstats, const float* coef, const floa
                              int groups, int64_t spatial, float* coef2, float* dgamma, float* dbeta, void* stream);
 int b200unet_gn_bwd(const b200unet_tensor* dz, const b200unet_tensor* x, const float* coef, const float* coef2,
                     const b200unet_tensor* add1, const b200unet_tensor* add2, const b200unet_tensor* dx, void* stream);
+
+/* ---- post-activation blocks (conv -> norm -> act: MONAI UnetBasicBlock): gradient through the activation of
+ * a = act(A c + B):  dz = (g1 [+ g2]) * act'(A c + B),  bstats[n][ch] += (sum dz, sum dz * xhat)  -> b200unet_gn_bwd */
+int b200unet_act_bwd(const b200unet_tensor* g1, const b200unet_tensor* g2, const b200unet_tensor* c, const float* coef, float slope,
+                     const b200unet_tensor* dz, double* bstats, int bstats_ld, void* stream);
 
 /* ---- F.interpolate(scale_factor=2, mode="trilinear", align_corners=False) (decoder.py:105-106), fwd + adjoint */
 int b200unet_upsample2x_fwd(const b200unet_tensor* x, const b200unet_tensor* y, double* stats, int stats_ld,
@@ -157,6 +164,11 @@ typedef struct b200unet_net_desc {
   int32_t activation;         /* 0 none, 1 sigmoid, 2 softmax (variational.py:62-68) */
   int32_t split_precision;    /* 0 = bf16 single pass (perf), 1 = hi/lo split, 3 MMAs (parity) */
   int32_t batch, depth, height, width;
+  int32_t arch;               /* 0 = the reference's UNet3D (above); 1 = MONAI DynUNet blocks as trained by
+                                 examples/brats2020/brats2020_config.json:2-107: n_levels = len(filters), kernel 3, strides
+                                 1,2,2,..., transposed-conv upsampling kernel = stride = 2, InstanceNorm(affine) + LeakyReLU */
+  int32_t filters[8];         /* arch 1: channels per level (multiples of 8) */
+  float act_slope;            /* arch 1: negative slope of the LeakyReLU (0.01) */
   int32_t inference_only;     /* 1 = forward-only plan (volumetric.py:131-150 runs under no_grad): no backward schedule, no
                                  backward buffers, forward temporaries are recycled -> a much smaller workspace */
 } b200unet_net_desc;

@@ -15,6 +15,7 @@ from oracle.prepost_oracle import one_hot_encode, label_map_from_one_hot, normal
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, HERE)
 from recipe_prepost import ONE_HOT_CASES, LABEL_MAP_CASES, label_map_input, prediction_input  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -46,6 +47,24 @@ def test_inferer_rejects_gradient_tracking_network(pkg):
     inf = pkg.predict.SlidingWindowInferer(roi_size=(8, 8, 8))
     with pytest.raises(RuntimeError, match="inference-only"):
         inf(torch.zeros(1, 1, 12, 12, 12, device=DEV), net)
+
+
+def test_inferer_identity_property_monai_cases(pkg):
+    """MONAI's own sliding-window unit test: ``compute = data + 1`` must return ``inputs + 1`` for every tiling."""
+    from test_oracle_monai_cases import MONAI_SW_CASES
+    for shape, roi, swb, overlap, mode in MONAI_SW_CASES:
+        x = torch.randn(shape, generator=torch.Generator().manual_seed(0)).to(DEV)
+        inf = pkg.predict.SlidingWindowInferer(roi_size=roi, sw_batch_size=swb, overlap=overlap, mode=mode)
+        with torch.no_grad():
+            out = inf(x, lambda data: data + 1)
+        assert float((out - (x + 1)).abs().max()) < 1e-4, (shape, roi, mode)
+
+
+def test_dice_kernel_reproduces_monai_published_values(pkg):
+    from test_oracle_monai_cases import MONAI_DICE_CASES
+    for kw, x, t, expected in MONAI_DICE_CASES:
+        loss = pkg.DiceLoss(**kw)(x.to(DEV), t.to(DEV))
+        assert abs(float(loss) - expected) < 2e-6, kw
 
 
 # ------------------------------------------------------------------------------------------------ one-hot / label map / z-score

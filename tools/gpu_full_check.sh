@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r02}
-timeout 2400 python -m pytest tests -m gpu -q -x --durations=15 2>&1 | tail -60 > gpurun_out/${TAG}_pytest.log
+timeout 2400 python -m pytest tests -m gpu -q --durations=15 2>&1 | tail -60 > gpurun_out/${TAG}_pytest.log
 tail -25 gpurun_out/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.log
 timeout 900 python tools/bf16_grad_study.py > gpurun_out/${TAG}_bf16_study.log 2>&1; tail -c 1500 gpurun_out/${TAG}_bf16_study.log
