@@ -82,6 +82,7 @@ int b200unet_conv3d_wgrad(const b200unet_tensor* a, const b200unet_tensor* dy, i
                           float* dw, void* stream) {
   NOT_NULL(a); NOT_NULL(dy); NOT_NULL(dw);
   WgradOp op;
+  memset(&op, 0, sizeof(op));
   op.a = to_act(a); op.dy = to_act(dy); op.ksz = ksz; op.stride = stride; op.nopad = ksz == 2 ? 1 : 0; op.Cip = cip; op.Cop = cop; op.dw = dw;
   return launch_wgrad(op, to_stream(stream));
 }
@@ -148,10 +149,11 @@ int b200unet_head_fwd(const b200unet_tensor* x, const float* w, int n_out, int a
   NOT_NULL(x); NOT_NULL(w); NOT_NULL(logits);
   return launch_head_fwd(to_act(x), w, n_out, act, logits, to_stream(stream));
 }
+size_t b200unet_head_bwd_scratch_bytes(int n_out, int c) { return head_bwd_scratch_bytes(n_out, c); }
 int b200unet_head_bwd(const b200unet_tensor* x, const float* w, int n_out, const float* dlogits,
-                      const b200unet_tensor* dx, float* dw, void* stream) {
-  NOT_NULL(x); NOT_NULL(w); NOT_NULL(dlogits); NOT_NULL(dx); NOT_NULL(dw);
-  return launch_head_bwd(to_act(x), w, n_out, dlogits, to_act(dx), dw, to_stream(stream));
+                      const b200unet_tensor* dx, float* dw, float* scratch, void* stream) {
+  NOT_NULL(x); NOT_NULL(w); NOT_NULL(dlogits); NOT_NULL(dx); NOT_NULL(dw); NOT_NULL(scratch);
+  return launch_head_bwd(to_act(x), w, n_out, dlogits, to_act(dx), dw, to_stream(stream), scratch);
 }
 
 int b200unet_dice_fwd(const float* logits, const void* target, int n, int c, int64_t spatial, int flags,

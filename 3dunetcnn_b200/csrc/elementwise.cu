@@ -866,7 +866,7 @@ int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float
 // (n_out x 8) stay in registers and are reduced once at the end (shuffle over lanes that share the chunk -> smem -> global).
 template <int NO>
 __global__ void k_head_bwd(Act x, const float* __restrict__ w, const float* __restrict__ dlogits, Act dx,
-                           float* __restrict__ dw) {
+                           float* __restrict__ part) {
   extern __shared__ float sm[];  // sw [NO][C] | sdw [NO][C]
   float* sw = sm;
   float* sdw = sm + NO * x.C;
@@ -923,29 +923,40 @@ __global__ void k_head_bwd(Act x, const float* __restrict__ w, const float* __re
       store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
     }
   }
-  // lanes l and l' share the chunk iff l % c8n == l' % c8n (c8n is a power of two <= 32 here, else fall back to atomics)
-  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
+  // Block reduction in a FIXED order (no floating-point atomics): per-thread partials -> shared memory -> thread i sums the
+  // threads that own channel i's chunk (t = c8, c8 + c8n, ...) -> this block's slot of `part`; k_sum_slots then adds the
+  // block slots in order.  The weight gradient of the head is bit-reproducible run to run.
+  float* s_tmp = sdw + NO * x.C;   // [blockDim.x][8]
 #pragma unroll
-  for (int o = 0; o < NO; ++o)
+  for (int o = 0; o < NO; ++o) {
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float p = pdw[o][j];
-      if (pow2) {
-        for (int off = 16; off >= c8n; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-        if ((threadIdx.x & 31) < c8n) atomicAdd(&sdw[o * x.C + c8 * 8 + j], p);
-      } else {
-        atomicAdd(&sdw[o * x.C + c8 * 8 + j], p);
-      }
+    for (int j = 0; j < 8; ++j) s_tmp[threadIdx.x * 8 + j] = pdw[o][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < x.C; i += blockDim.x) {
+      const int ch = i >> 3, j = i & 7;
+      float acc = 0.f;
+      for (int t = ch; t < (int)blockDim.x; t += c8n) acc += s_tmp[t * 8 + j];
+      part[(long long)blockIdx.x * NO * x.C + o * x.C + i] = acc;
     }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NO * x.C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+  }
 }
 
+__global__ void k_sum_slots(const float* __restrict__ part, int slots, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < slots; ++s) acc += part[(long long)s * n + i];
+  out[i] = acc;
+}
+
+size_t head_bwd_scratch_bytes(int n_out, int C) { return (size_t)1184 * n_out * C * sizeof(float); }
+
 int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
-                    cudaStream_t st) {
+                    cudaStream_t st, float* scratch) {
   B200_REQUIRE(n_out >= 1 && n_out <= 8, E_UNSUPPORTED, "head_bwd: n_outputs=%d > 8 unsupported", n_out);
   B200_REQUIRE(x.C % 8 == 0 && dx.C == x.C, E_INVALID, "head_bwd: channel mismatch");
-  B200_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * x.C, st));
+  B200_REQUIRE(scratch != nullptr, E_INVALID, "head_bwd: needs head_bwd_scratch_bytes() of scratch");
   const int c8n = x.C / 8;
   int threads = 256;
   while (threads % c8n) threads += 32;
@@ -953,14 +964,16 @@ int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogit
   long long total = x.voxels() * c8n;
   int blocks = ew_blocks(total, threads);
   if (blocks > 1184) blocks = 1184;
-  const size_t smem = 2 * n_out * x.C * sizeof(float);
+  const size_t smem = (2 * n_out * x.C + (size_t)threads * 8) * sizeof(float);
 #define B200_HEAD_CASE(no) \
-  case no: k_head_bwd<no><<<blocks, threads, smem, st>>>(x, w, dlogits, dx, dw); break;
+  case no: k_head_bwd<no><<<blocks, threads, smem, st>>>(x, w, dlogits, dx, scratch); break;
   switch (n_out) {
     B200_HEAD_CASE(1) B200_HEAD_CASE(2) B200_HEAD_CASE(3) B200_HEAD_CASE(4)
     B200_HEAD_CASE(5) B200_HEAD_CASE(6) B200_HEAD_CASE(7) B200_HEAD_CASE(8)
   }
 #undef B200_HEAD_CASE
+  B200_CHECK_CUDA(cudaGetLastError());
+  k_sum_slots<<<ceil_div(n_out * x.C, 128), 128, 0, st>>>(scratch, blocks, n_out * x.C, dw);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -31,7 +31,8 @@ int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* d
 int launch_act_bwd(const Act& g1, const Act* g2, const Act& c, const float* coef, float slope, const Act& dz, double* bstats,
                    int bstats_ld, cudaStream_t st);
 int launch_head_bwd(const Act& x, const float* w, int n_out, const float* dlogits, const Act& dx, float* dw,
-                    cudaStream_t st);
+                    cudaStream_t st, float* scratch);   // scratch: head_bwd_scratch_bytes(n_out, C) (per-block partial sums)
+size_t head_bwd_scratch_bytes(int n_out, int C);
 int launch_pack_weights(const float* w, int Co, int Ci, int Cop, int Cip, int T, int mode, bf16* hi, bf16* lo,
                         cudaStream_t st);
 int launch_unpack_wgrad(const float* g, int Co, int Ci, int Cop, int Cip, int T, int mode, float* out,
@@ -135,7 +136,15 @@ struct WgradOp {
   int Cip;     // pitch of the [T][Cip][Cop] fp32 accumulator rows
   int Cop;
   float* dw;   // fp32 [T][Cip][Cop]; accumulated with atomics, caller zero-fills
+  // deterministic mode (optional): the split-K CTAs store their partial sums into part[split][T][Cip][Cop] instead of
+  // accumulating into dw with atomics; launch_wgrad_reduce then sums the slots in a fixed order.
+  float* part;
+  size_t part_bytes;
+  int* part_splits;   // out: number of slots written
 };
+int launch_wgrad_reduce(const float* part, int splits, long long elems, float* dw, cudaStream_t st);   // dw = sum_s part[s]
+// worst-case bytes of the partial buffer for this shape on a device with num_sms SMs (host-only shape logic)
+size_t wgrad_partial_bytes(const WgradOp& op, int num_sms);
 int launch_wgrad(const WgradOp& op, cudaStream_t st);              // dispatcher: halo-resident kernel when eligible
 int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st);
 bool wgrad_halo_eligible(const WgradOp& op);

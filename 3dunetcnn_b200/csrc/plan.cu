@@ -134,6 +134,9 @@ struct b200unet_plan {
   double macs[CAT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // algorithmic MACs per forward+backward pass, by category
   size_t drop_off = 0;      // [N][base_width] floats: copy of the dropout scale of the last forward
   bool have_drop = false;
+  bool deterministic = false;   // weight gradients: per-split partial sums + fixed-order reduction instead of fp32 atomics
+  size_t head_part_off = 0;   // per-block partial sums of the head weight gradient (fixed-order reduction)
+  size_t wg_part_off = 0, wg_part_bytes = 0;   // scratch shared by all weight-gradient launches (stream-ordered)
   float slope = 0.f;        // negative slope of the activation (0 = ReLU: UNet3D; 0.01 = LeakyReLU: DynUNet)
   bool infer = false;       // forward-only plan: no backward schedule / buffers, forward temporaries are recycled
   std::vector<std::pair<size_t, std::pair<size_t, size_t>>> free_bufs;   // (bytes, (off_hi, off_lo)) of released buffers
@@ -413,17 +416,56 @@ static void emit_conv_fwd(Plan& P, int ci, TRef a, int ci2, TRef a2, TRef res, T
 }
 
 // ---- backward op emitters
+static int plan_num_sms() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    return sms;
+  cudaGetLastError();   // planning on a host without a GPU: assume a B200
+  return 148;
+}
+
+static void size_wgrad_partials(Plan& P, const Act& a, const Act& dy, int ksz, int stride, int nopad, int Cip, int Cop) {
+  if (!P.deterministic) return;
+  WgradOp op;
+  memset(&op, 0, sizeof(op));
+  op.a = a; op.dy = dy; op.ksz = ksz; op.stride = stride; op.nopad = nopad; op.Cip = Cip; op.Cop = Cop;
+  const size_t need = wgrad_partial_bytes(op, plan_num_sms());
+  if (need > P.wg_part_bytes) P.wg_part_bytes = need;
+}
+
+static Act shape_act(const Plan& P, TRef t) {
+  const Buf& b = P.bufs[t.buf];
+  return make_act(nullptr, nullptr, b.N, b.D, b.H, b.W, t.c, b.C);
+}
+
+// runs one weight-gradient op; in deterministic mode through the partial-sum scratch + the fixed-order reduction
+static int run_wgrad(Plan& P, RunCtx& cx, WgradOp& op) {
+  if (!P.deterministic) {
+    LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
+    return OK;
+  }
+  int splits = 0;
+  op.part = reinterpret_cast<float*>(cx.ws + P.wg_part_off);
+  op.part_bytes = P.wg_part_bytes;
+  op.part_splits = &splits;
+  LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
+  B200_REQUIRE(splits >= 1, E_INVALID, "plan: internal: deterministic weight gradient wrote no partial slots");
+  LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad_reduce(op.part, splits, (long long)op.ksz * op.ksz * op.ksz * op.Cip * op.Cop, op.dw, cx.st));
+  return OK;
+}
+
 static void emit_wgrad(Plan& P, int ci, TRef a, TRef dy) {
   P.macs[CAT_CONV_WGRAD] += conv_macs(P, ci, dy);
+  size_wgrad_partials(P, shape_act(P, a), shape_act(P, dy), P.convs[ci].ksz, P.convs[ci].stride, 0, P.convs[ci].Cip, P.convs[ci].Cop);
   push_op(P.bwd, "wgrad " + P.convs[ci].name + " " + shape_of(P, a) + " x " + shape_of(P, dy), [&P, ci, a, dy](RunCtx& cx) -> int {
     const ConvLayer& c = P.convs[ci];
     WgradOp op;
+  memset(&op, 0, sizeof(op));
     op.a = act_of(P, cx, a);
     op.dy = act_of(P, cx, dy);
     op.ksz = c.ksz; op.stride = c.stride; op.nopad = 0; op.Cip = c.Cip; op.Cop = c.Cop;
     op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
-    LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
-    return OK;
+    return run_wgrad(P, cx, op);
   });
 }
 
@@ -717,7 +759,8 @@ static int build_unet3d(Plan& P) {
     TRef gg = g;
     push_op(P.bwd, "head_bwd", [&P, Xfinal, gg](RunCtx& cx) -> int {
       LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits,
-                                   act_of(P, cx, gg), cx.grads[P.head_param], cx.st));
+                                   act_of(P, cx, gg), cx.grads[P.head_param], cx.st,
+                                   reinterpret_cast<float*>(cx.ws + P.head_part_off)));
       return OK;
     });
   }
@@ -800,6 +843,8 @@ static int finish_build(Plan& P) {
   P.drop_off = P.alloc(sizeof(float) * N * (d.base_width > 0 ? d.base_width : 8));
   P.stats_off = P.alloc(P.stats_bytes);
   P.bz_off = P.alloc(P.bz_bytes);
+  if (P.wg_part_bytes) P.wg_part_off = P.alloc(P.wg_part_bytes);
+  if (!P.infer) P.head_part_off = P.alloc(head_bwd_scratch_bytes(d.n_outputs, d.arch == 1 ? d.filters[0] : d.base_width));
   for (size_t i = 0; i < P.convs.size(); ++i)
     B200_REQUIRE(P.convs[i].pw >= 0, E_INVALID, "plan: internal: conv %d has no parameter", (int)i);
   for (const ConvLayer& c : P.convs) {
@@ -1038,7 +1083,7 @@ static int build_dynunet(Plan& P) {
     TRef gg = g;
     push_op(P.bwd, "head_bwd", [&P, Xfinal, gg, head_bias](RunCtx& cx) -> int {
       LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits, act_of(P, cx, gg),
-                                             cx.grads[P.head_param], cx.st));
+                                             cx.grads[P.head_param], cx.st, reinterpret_cast<float*>(cx.ws + P.head_part_off)));
       const Buf& b = P.bufs[Xfinal.buf];
       LAUNCHED(cx, CAT_HEAD, launch_head_dbias(cx.dlogits, b.N, P.d.n_outputs, (long long)b.D * b.H * b.W, cx.grads[head_bias], cx.st));
       return OK;
@@ -1054,17 +1099,18 @@ static int build_dynunet(Plan& P) {
     // input of the transposed convolution: the activated output of the stage below (or of the bottleneck)
     const TRef Xlow = (lo == L - 1) ? enc[lo].out : dec[lo].out;
     P.macs[CAT_CONV_WGRAD] += (double)N * Ds[lo] * Hs[lo] * Ws[lo] * F[lo] * F[hi] * 8;
+    size_wgrad_partials(P, shape_act(P, dU), shape_act(P, Xlow), 2, 2, 1, P.convs[ci].Cop, P.convs[ci].Cip);
     push_op(P.bwd, "wgrad_up2 " + P.convs[ci].name, [&P, ci, Xlow, dU](RunCtx& cx) -> int {
       // dW[ci][co][t] = sum_j X[j][ci] dU[2j + t][co]: the weight gradient of the kernel-2 stride-2 convolution that maps the
       // FINE grid (dU, "input", channels co) to the COARSE grid (X, "output gradient", channels ci): accumulator [T][pad(Co)][pad(Ci)]
       const ConvLayer& c = P.convs[ci];
       WgradOp op;
+  memset(&op, 0, sizeof(op));
       op.a = act_of(P, cx, dU);
       op.dy = act_of(P, cx, Xlow);
       op.ksz = 2; op.stride = 2; op.nopad = 1; op.Cip = c.Cop; op.Cop = c.Cip;
       op.dw = reinterpret_cast<float*>(cx.ws + P.bz_off + c.dw);
-      LAUNCHED(cx, CAT_CONV_WGRAD, launch_wgrad(op, cx.st));
-      return OK;
+      return run_wgrad(P, cx, op);
     });
     const Buf lb = P.bufs[Xlow.buf];
     TRef gX = full(P, new_buf(P, N, lb.D, lb.H, lb.W, F[lo]));
@@ -1116,6 +1162,7 @@ int b200unet_plan_create(const b200unet_net_desc* desc, b200unet_plan** out) {
   P->d = *desc;
   P->split = desc->split_precision != 0;
   P->infer = desc->inference_only != 0;
+  P->deterministic = desc->deterministic != 0;
   if (P->d.norm_groups <= 0) P->d.norm_groups = 8;
   if (P->d.feature_dilation <= 0) P->d.feature_dilation = 2;
   int s = build(*P);

@@ -39,6 +39,8 @@ struct WgradArgs {
   int splits;
   int npass;
   float* dw;
+  float* part;             // deterministic mode: per-split partial sums [splits][T][Cip][Cop] (plain stores) instead of atomics
+  long long part_stride;   // elements per split
 };
 
 constexpr int WG_A_STAGES = 4;
@@ -193,21 +195,24 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
       const int u = (q0 + qi) * Cfg::BPM + row / CB;
       const int tap = u / p.nci, cic = u % p.nci;
       const int ci = cic * CB + row % CB;
-      const bool row_ok = (u < p.units) && (ci < p.Ci) && (kb1 > kb0);
+      const bool in_range = (u < p.units) && (ci < p.Ci);
+      const bool has_work = kb1 > kb0;
+      float* const base = p.part ? p.part + (long long)split * p.part_stride : p.dw;
 #pragma unroll 1
       for (int j = 0; j < BN / 16; ++j) {
         uint32_t r[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + qi * BN + j * 16, r);
         tmem_ld_wait();
         const int c = co0 + j * 16;
-        if (row_ok) {
-          float* dst = p.dw + ((long long)tap * p.Cip + ci) * p.Cop + c;
+        if (in_range && (has_work || p.part)) {
+          float* dst = base + ((long long)tap * p.Cip + ci) * p.Cop + c;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             if (c + i + 3 < p.Cop) {
               float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
                                      __uint_as_float(r[i + 3]));
-              atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+              if (p.part) *reinterpret_cast<float4*>(dst + i) = has_work ? v : make_float4(0.f, 0.f, 0.f, 0.f);   // every split writes its slot
+              else atomicAdd(reinterpret_cast<float4*>(dst + i), v);
             }
           }
         }
@@ -236,9 +241,60 @@ static int launch_wg(const WgradMaps& maps, const WgradArgs& a, dim3 grid, cudaS
   return OK;
 }
 
+// split-K factor of the streaming kernel for this shape (shared by the launcher and the deterministic-mode buffer sizing)
+static int wgrad_stream_splits(const WgradOp& op) {
+  const Act& A = op.a;
+  const Act& Y = op.dy;
+  int tw, th, td;
+  pick_tile_w(Y.W, Y.H, Y.D, tw, th, td);
+  const int ntaps = op.ksz * op.ksz * op.ksz;
+  const int CB = A.C > 32 ? 64 : A.C > 16 ? 32 : 16;
+  const int BN = Y.C > 64 ? 128 : Y.C > 32 ? 64 : Y.C > 16 ? 32 : 16;
+  const int qtiles = ceil_div(ntaps * ceil_div(A.C, CB), 128 / CB);
+  int qt = 512 / BN;
+  if (qt > qtiles) qt = qtiles;
+  const int groups = ceil_div(qtiles, qt);
+  const int cotiles = ceil_div(Y.C, BN);
+  const int kblocks = Y.N * ceil_div(Y.D, td) * ceil_div(Y.H, th) * ceil_div(Y.W, tw);
+  int splits = 148 / (groups * cotiles);
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  return splits;
+}
+
+__global__ void k_wgrad_reduce(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ dw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = part[i];
+    for (int s = 1; s < splits; ++s) {   // fixed order: bit-reproducible
+      const float4 v = part[(long long)s * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dw[i] = acc;
+  }
+}
+
+int launch_wgrad_reduce(const float* part, int splits, long long elems, float* dw, cudaStream_t st) {
+  B200_REQUIRE(part && dw && splits >= 1 && elems % 4 == 0, E_INVALID, "wgrad_reduce: bad argument");
+  const long long n4 = elems / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_wgrad_reduce<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(part), splits, n4, reinterpret_cast<float4*>(dw));
+  B200_CHECK_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int wgrad_halo_splits(const WgradOp& op, int num_sms);   // wgrad_halo.cu
+
+size_t wgrad_partial_bytes(const WgradOp& op, int num_sms) {
+  static const bool no_halo = getenv("B200UNET_NO_HALO_WGRAD") != nullptr;
+  const long long elems = (long long)op.ksz * op.ksz * op.ksz * op.Cip * op.Cop;
+  const int splits = (!no_halo && wgrad_halo_eligible(op)) ? wgrad_halo_splits(op, num_sms) : wgrad_stream_splits(op);
+  return (size_t)splits * elems * sizeof(float);
+}
+
 int launch_wgrad(const WgradOp& op, cudaStream_t st) {
   static const bool no_halo = getenv("B200UNET_NO_HALO_WGRAD") != nullptr;
-  if (wgrad_1x1_narrow_eligible(op)) return launch_wgrad_1x1_narrow(op, st);
+  if (!op.part && wgrad_1x1_narrow_eligible(op)) return launch_wgrad_1x1_narrow(op, st);   // (the SIMT path reduces with atomics)
   if (!no_halo && wgrad_halo_eligible(op)) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -287,12 +343,17 @@ int launch_wgrad_streaming(const WgradOp& op, cudaStream_t st) {
   a.qt = ceil_div(a.qtiles, groups);
   const int cotiles = ceil_div(Y.C, BN);
   a.kblocks = a.N * a.tiles_d * a.tiles_h * a.tiles_w;
-  int splits = 148 / (groups * cotiles);
-  if (splits < 1) splits = 1;
-  if (splits > a.kblocks) splits = a.kblocks;
+  const int splits = wgrad_stream_splits(op);
   a.splits = splits;
   a.npass = split ? 3 : 1;
   a.dw = op.dw;
+  if (op.part) {
+    a.part = op.part;
+    a.part_stride = (long long)a.ntaps * op.Cip * op.Cop;
+    B200_REQUIRE((size_t)splits * a.part_stride * sizeof(float) <= op.part_bytes, E_INVALID,
+                 "wgrad: deterministic partial buffer too small (%d splits)", splits);
+    if (op.part_splits) *op.part_splits = splits;
+  }
   B200_TRY(make_act_map(&maps.a[0], A.hi, A.N, A.D, A.H, A.W, A.C, A.ld, CB, a.tw, a.th, a.td, op.stride,
                         swz_for_bytes(CB * 2), A.vD, A.vH, A.vW));
   B200_TRY(make_act_map(&maps.dy[0], Y.hi, Y.N, Y.D, Y.H, Y.W, Y.C, Y.ld, CBN, a.tw, a.th, a.td, 1,

@@ -39,6 +39,8 @@ struct WgHaloArgs {
   int npass;
   int hsplit;     // halo box loaded as (TD+2)*hsplit TMA boxes, dY tile as TD boxes (more requests in flight)
   float* dw;
+  float* part;             // deterministic mode: per-split partial sums (plain stores) instead of atomics
+  long long part_stride;
 };
 
 template <int KC, int BN, int TD>
@@ -194,7 +196,9 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
     tc_fence_after();
     const int kw = row / KC;
     const int ci = kc * KC + row % KC;
-    const bool row_ok = (kw < 3) && (ci < p.Ci) && (t1 > t0);
+    const bool in_range = (kw < 3) && (ci < p.Ci);
+    const bool has_work = t1 > t0;
+    float* const base = p.part ? p.part + (long long)blockIdx.x * p.part_stride : p.dw;
     for (int qi = 0; qi < nq; ++qi) {
       for (int blk = 0; blk < 3; ++blk) {
         const int tap = ((2 - blk) * 3 + (q0 + qi)) * 3 + kw;   // column block blk holds kd = 2 - blk
@@ -204,14 +208,15 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
           tmem_ld16(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + (qi * 3 + blk) * BN + j * 16, r);
           tmem_ld_wait();
           const int c = co0 + j * 16;
-          if (row_ok) {
-            float* dst = p.dw + ((long long)tap * p.Cip + ci) * p.Cop + c;
+          if (in_range && (has_work || p.part)) {
+            float* dst = base + ((long long)tap * p.Cip + ci) * p.Cop + c;
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               if (c + i + 3 < p.Cop) {
                 float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
                                        __uint_as_float(r[i + 3]));
-                atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+                if (p.part) *reinterpret_cast<float4*>(dst + i) = has_work ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+                else atomicAdd(reinterpret_cast<float4*>(dst + i), v);
               }
             }
           }
@@ -246,6 +251,23 @@ bool wgrad_halo_eligible(const WgradOp& op) {
   return op.ksz == 3 && op.stride == 1 && op.dy.W >= 8 && op.dy.H >= 16;
 }
 
+int wgrad_halo_splits(const WgradOp& op, int num_sms) {
+  const Act& A = op.a;
+  const Act& Y = op.dy;
+  const int KC = A.C > 16 ? 32 : 16;
+  const int BN = Y.C > 32 ? 64 : Y.C > 16 ? 32 : 16;
+  const int TD = (BN <= 32 && Y.D >= 4) ? 4 : 2;
+  const int tiles_total = Y.N * ceil_div(Y.D, TD) * ceil_div(Y.H, 16) * ceil_div(Y.W, 8);
+  int qt = 512 / (3 * BN);
+  if (qt > 3) qt = 3;
+  const int gpk = ceil_div(3, qt);
+  const int roles = ceil_div(A.C, KC) * gpk * ceil_div(Y.C, BN);
+  int splits = num_sms / roles;
+  if (splits < 1) splits = 1;
+  if (splits > tiles_total) splits = tiles_total;
+  return splits;
+}
+
 int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
   const Act& A = op.a;
   const Act& Y = op.dy;
@@ -274,13 +296,17 @@ int launch_wgrad_halo(const WgradOp& op, int num_sms, cudaStream_t st) {
   a.gpk = ceil_div(3, a.qt);
   a.qt = ceil_div(3, a.gpk);
   const int cotiles = ceil_div(Y.C, BN);
-  const int roles = a.nkc * a.gpk * cotiles;
-  int splits = num_sms / roles;
-  if (splits < 1) splits = 1;
-  if (splits > a.tiles_total) splits = a.tiles_total;
+  const int splits = wgrad_halo_splits(op, num_sms);
   a.splits = splits;
   a.npass = split ? 3 : 1;
   a.dw = op.dw;
+  if (op.part) {
+    a.part = op.part;
+    a.part_stride = (long long)27 * op.Cip * op.Cop;
+    B200_REQUIRE((size_t)splits * a.part_stride * sizeof(float) <= op.part_bytes, E_INVALID,
+                 "wgrad_halo: deterministic partial buffer too small (%d splits)", splits);
+    if (op.part_splits) *op.part_splits = splits;
+  }
   int hsplit = KC == 32 ? 2 : 1;
   if (const char* e = getenv("B200UNET_HALO_HSPLIT")) {
     const int v = atoi(e);

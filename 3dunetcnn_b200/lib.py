@@ -40,7 +40,7 @@ class NetDesc(C.Structure):
                 ("use_transposed_convolutions", C.c_int32), ("activation", C.c_int32),
                 ("split_precision", C.c_int32), ("batch", C.c_int32), ("depth", C.c_int32), ("height", C.c_int32),
                 ("width", C.c_int32), ("arch", C.c_int32), ("filters", C.c_int32 * 8), ("act_slope", C.c_float),
-                ("inference_only", C.c_int32)]
+                ("deterministic", C.c_int32), ("inference_only", C.c_int32)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -87,8 +87,9 @@ _SIGS = {
     "b200unet_upsample2x_bwd": (C.c_int, [C.POINTER(Tensor5), C.POINTER(Tensor5), C.c_void_p]),
     "b200unet_zero_insert": (C.c_int, [C.POINTER(Tensor5), C.POINTER(Tensor5), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200unet_head_fwd": (C.c_int, [C.POINTER(Tensor5), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200unet_head_bwd_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200unet_head_bwd": (C.c_int, [C.POINTER(Tensor5), C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Tensor5),
-                                    C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200unet_dice_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200unet_dice_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
@@ -336,8 +337,10 @@ def head_fwd(x: Act, w: torch.Tensor, n_out: int, act: int, logits: torch.Tensor
 
 
 def head_bwd(x: Act, w, n_out, dlogits, dx: Act, dw) -> None:
-    check(load_library().b200unet_head_bwd(C.byref(x.ct()), w.data_ptr(), n_out, dlogits.data_ptr(), C.byref(dx.ct()),
-                                           dw.data_ptr(), stream_ptr()), "head_bwd")
+    lib = load_library()
+    scratch = torch.empty(int(lib.b200unet_head_bwd_scratch_bytes(n_out, x.c)), dtype=torch.uint8, device=x.hi.device)
+    check(lib.b200unet_head_bwd(C.byref(x.ct()), w.data_ptr(), n_out, dlogits.data_ptr(), C.byref(dx.ct()),
+                                dw.data_ptr(), scratch.data_ptr(), stream_ptr()), "head_bwd")
 
 
 def dice_flags(sigmoid=True, squared_pred=False, jaccard=False, batch=False, include_background=True,

@@ -158,7 +158,12 @@ class _PlanModel(nn.Module):
     cache of whole-network plans keyed by input shape, gradient placement.  Subclasses provide ``_param_spec_cpu`` (ordered
     (key, shape) list), ``_net_desc`` (the library's network descriptor) and ``_init_tensor``."""
 
-    def _setup(self, precision: Optional[str]) -> None:
+    def _setup(self, precision: Optional[str], deterministic: Optional[bool] = None) -> None:
+        # deterministic: weight gradients reduced without floating-point atomics (per-split partial sums + fixed-order sum):
+        # bit-identical gradients run to run at ~3 % of the step time; B200UNET_DETERMINISTIC=1 sets the default
+        if deterministic is None:
+            deterministic = os.environ.get("B200UNET_DETERMINISTIC", "0") == "1"
+        self.deterministic = bool(deterministic)
         precision = precision or os.environ.get("B200UNET_PRECISION", "bf16")
         if precision not in ("bf16", "split"):
             raise ValueError("precision must be 'bf16' or 'split'")
@@ -191,6 +196,7 @@ class _PlanModel(nn.Module):
         if plan is None:
             desc = self._net_desc(n, d, h, w)
             desc.inference_only = int(bool(inference_only))
+            desc.deterministic = int(self.deterministic and not inference_only)
             plan = _Plan(desc, x.device)
             spec = plan.param_spec()
             mine = [(k, tuple(p.shape)) for k, p in zip(self._keys, self.ordered_parameters())]
@@ -272,7 +278,7 @@ class UNet3D(_PlanModel):
                  feature_dilation=2, downsampling_stride=2, interpolation_mode="trilinear", encoder_class=None,
                  decoder_class=None, n_outputs=1, layer_widths=None, decoder_mirrors_encoder=False, activation=None,
                  use_transposed_convolutions=False, kernel_size=3, precision: Optional[str] = None,
-                 dropout: float = 0.2, norm_groups: int = 8):
+                 dropout: float = 0.2, norm_groups: int = 8, deterministic: Optional[bool] = None):
         super().__init__()
         if downsampling_stride != 2:
             raise NotImplementedError("B200 UNet3D: downsampling_stride=%r (only 2 is implemented)" % (downsampling_stride,))
@@ -303,7 +309,7 @@ class UNet3D(_PlanModel):
         self.dropout_p = float(dropout)                          # myronenko.py:85 (hard-wired 0.2 in the reference)
         self.norm_groups = int(norm_groups)
         self.dropout_width = self.base_width
-        self._setup(precision)                                   # parameters under the reference's keys
+        self._setup(precision, deterministic)                    # parameters under the reference's keys
 
     @staticmethod
     def _init_tensor(key, t, shapes):
@@ -437,7 +443,7 @@ class DynUNet(_PlanModel):
     def __init__(self, spatial_dims=3, in_channels=1, out_channels=1, kernel_size=None, strides=None, upsample_kernel_size=None,
                  filters=None, dropout=None, norm_name=("INSTANCE", {"affine": True}),
                  act_name=("leakyrelu", {"inplace": True, "negative_slope": 0.01}), deep_supervision=False, deep_supr_num=1,
-                 res_block=False, trans_bias=False, precision: Optional[str] = None):
+                 res_block=False, trans_bias=False, precision: Optional[str] = None, deterministic: Optional[bool] = None):
         super().__init__()
 
         def triple(v):
@@ -480,7 +486,7 @@ class DynUNet(_PlanModel):
         self.n_features, self.n_outputs = self.in_channels, self.out_channels
         self.filters = filters
         self.act_slope = float(act_kw.get("negative_slope", 0.01)) if act == "leakyrelu" else 0.0
-        self._setup(precision)
+        self._setup(precision, deterministic)
 
     def _param_spec_cpu(self):
         spec = []

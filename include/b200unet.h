@@ -111,8 +111,10 @@ int b200unet_zero_insert(const b200unet_tensor* x, const b200unet_tensor* z, int
 
 /* ---- final 1x1x1 convolution to NCDHW fp32 logits (variational.py:59-60,84-86); act: 0 none 1 sigmoid 2 softmax */
 int b200unet_head_fwd(const b200unet_tensor* x, const float* w, int n_out, int act, float* logits, void* stream);
+/* head_bwd reduces dw without floating-point atomics (bit-reproducible): `scratch` holds one partial per thread block */
+size_t b200unet_head_bwd_scratch_bytes(int n_out, int c);
 int b200unet_head_bwd(const b200unet_tensor* x, const float* w, int n_out, const float* dlogits,
-                      const b200unet_tensor* dx, float* dw, void* stream);
+                      const b200unet_tensor* dx, float* dw, float* scratch, void* stream);
 
 /* ---- Dice criterion (monai.losses.DiceLoss as configured by script_utils.py:61-77).
  * flags: bit0 sigmoid, bit1 squared_pred, bit2 jaccard, bit3 batch, bit4 exclude background, bit5 reduction=sum,
@@ -169,6 +171,8 @@ typedef struct b200unet_net_desc {
                                  1,2,2,..., transposed-conv upsampling kernel = stride = 2, InstanceNorm(affine) + LeakyReLU */
   int32_t filters[8];         /* arch 1: channels per level (multiples of 8) */
   float act_slope;            /* arch 1: negative slope of the LeakyReLU (0.01) */
+  int32_t deterministic;      /* 1 = weight gradients without floating-point atomics: the split-K CTAs write per-split partial
+                                 sums, a second kernel adds them in a fixed order (bit-identical gradients run to run) */
   int32_t inference_only;     /* 1 = forward-only plan (volumetric.py:131-150 runs under no_grad): no backward schedule, no
                                  backward buffers, forward temporaries are recycled -> a much smaller workspace */
 } b200unet_net_desc;

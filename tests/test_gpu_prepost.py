@@ -182,6 +182,36 @@ def test_epoch_training_with_cuda_graph_and_short_last_batch(pkg):
     assert all(not torch.equal(a, b) for a, b in zip(before, model.parameters()) if a.numel() > 8)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "split"])
+def test_deterministic_mode_gives_bit_identical_gradients(pkg, precision):
+    """deterministic=True: the split-K weight gradients go through per-split partial sums + a fixed-order reduction (no fp32
+    atomics); two backward passes on the same inputs must agree BIT FOR BIT, and agree with the default (atomic) mode to
+    rounding.  Shapes large enough that every weight-gradient kernel splits K over several CTAs."""
+    kw = dict(n_features=4, n_outputs=3, base_width=16)
+    sd = make_state_dict(UNetConfig(**kw), seed=9)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 64, 64, 64, generator=g).to(DEV)
+    t = (torch.rand(2, 3, 64, 64, 64, generator=g) > 0.7).to(torch.uint8).to(DEV)
+    grads = {}
+    for det in (True, False):
+        model = pkg.UNet3D(precision=precision, deterministic=det, **kw).to(DEV)
+        model.load_state_dict(sd)
+        model.train()
+        model.set_dropout_scale(torch.ones(2, 16))
+        runs = []
+        for _ in range(2):
+            model.zero_grad(set_to_none=True)
+            pkg.DiceLoss(sigmoid=True)(model(x), t).backward()
+            runs.append([p.grad.clone() for p in model.ordered_parameters()])
+        if det:
+            for k, a, b in zip(model._keys, runs[0], runs[1]):
+                assert torch.equal(a, b), k
+        grads[det] = runs[0]
+    num = sum(float((a - b).double().pow(2).sum()) for a, b in zip(grads[True], grads[False])) ** 0.5
+    den = sum(float(b.double().pow(2).sum()) for b in grads[False]) ** 0.5
+    assert num / den < 1e-4
+
+
 def test_second_forward_before_backward_raises(pkg):
     model = pkg.UNet3D(precision="bf16", **KW).to(DEV).train()
     x1, _ = _batch(1)
