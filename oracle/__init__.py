@@ -8,9 +8,16 @@ the timed CPU baseline -- never as the thing shipped.
 Parity status: PINNED against the reference's own ``UNet3D`` class (imported
 in the build container through ``oracle/ref_loader.py``) by
 ``tests/golden/make_golden.py``; the resulting fixtures are committed under
-``tests/golden/``.  The Dice and sliding-window restatements follow MONAI's
-public definitions; MONAI itself is absent from this image, so those two are
-"parity unpinned" beyond hand-computed cases.
+``tests/golden/``.  ``prepost_oracle`` (label map <-> one-hot) is PINNED the same
+way against the reference's own ``unet3d/utils/one_hot.py``
+(``tests/golden/make_golden_prepost.py`` -> ``tests/golden/prepost.npz``).
+The Dice and sliding-window restatements follow MONAI's public definitions;
+MONAI itself is absent from this image, so they are held to known-answer cases
+of MONAI's own unit tests quoted from memory (``tests/test_oracle_monai_cases.py``:
+four Dice values to 6 digits, the ``compute = data + 1`` identity of the
+sliding-window inferer) -- pinned to published values, not to an importable
+MONAI.  ``dynunet_oracle`` and ``prepost_oracle.normalize_intensity`` restate
+MONAI code that no fixture here can reach: PARITY UNPINNED.
 """
 from .unet3d_oracle import (  # noqa: F401
     UNetConfig,
@@ -24,3 +31,4 @@ from .unet3d_oracle import (  # noqa: F401
     group_norm,
     conv3d_direct,
 )
+from . import prepost_oracle, dynunet_oracle  # noqa: F401,E402
