@@ -33,9 +33,19 @@ struct HaloCfg {
   static constexpr int HALO_TX = HALO_ROWS * RB;
   static constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;
   static constexpr int NHALO = 2;
-  static constexpr int TPB = BN <= 64 ? 3 : 1;              // taps per weight stage
+  static constexpr int TPB = BN <= 64 ? 3 : 1;              // taps per weight TMA box (the kd = 0,1,2 tiles of one (kh,kw))
   static constexpr int B_TAP = BN * KC * 2;                 // bytes of one tap's weight tile
-  static constexpr int B_TX = TPB * B_TAP;
+  static constexpr int B_BOX = TPB * B_TAP;                 // bytes of one weight TMA box
+  static constexpr int B_BOX_BYTES = (B_BOX + 1023) / 1024 * 1024;
+#ifdef B200_HALO_KWS1
+  static constexpr int KWS = 1;
+#else
+  // (kh,kw) boxes per weight stage.  BN <= 32: a stage holds the three kw boxes of one kh (36 instead of 12 MMAs between
+  // two stage hand-backs: the wait / fence / descriptor set-up of a hand-back cannot overlap the MMAs of the same issuing
+  // thread, ~150 cycles each -- tools/umma_rate.py: 76 cycles per MMA at 12 per stage vs 64 back to back)
+  static constexpr int KWS = (BN <= 32 && B_BOX % 1024 == 0) ? 3 : 1;
+#endif
+  static constexpr int B_TX = KWS * B_BOX;
   static constexpr int B_BYTES = (B_TX + 1023) / 1024 * 1024;
   static constexpr int NB_MAX = 24;
   static constexpr int CBO = BN < 64 ? BN : 64;             // channels per output staging box
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
   // K groups of one tile: source 0 = 27 taps per chunk (9 stages of TPB taps when TPB = 3), source 1 (optional
   // 1x1x1) = its centre tap per chunk
   const int groups0 = p.kchunks[0], groups1 = p.ntaps[1] ? p.kchunks[1] : 0;
-  constexpr int STAGES0 = 27 / Cfg::TPB;
+  constexpr int STAGES0 = 27 / (Cfg::TPB * Cfg::KWS);
 
   if (warp == 0 || warp == 10) {
     // ------------------------------------------------------------------ TMA producers (convergent, one lane issues)
@@ -170,9 +180,12 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
               const uint32_t s = bi % NB, ph = (bi / NB) & 1;
               mbar_wait(&b_empty[s], ph ^ 1);
               mbar_expect_tx_if(issue, &b_full[s], src == 0 ? Cfg::B_TX : Cfg::B_TAP);
-              if (Cfg::STK && src == 0)   // stage st = (kh,kw): the three kd taps through the 4-D (Cin, Cout, khkw, kd) view
-                tma_load_4d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0, st, 0);
-              else
+              if (Cfg::STK && src == 0) {   // box = (kh,kw): the three kd taps through the 4-D (Cin, Cout, khkw, kd) view
+#pragma unroll
+                for (int q = 0; q < Cfg::KWS; ++q)
+                  tma_load_4d_if(issue, smem_b + s * Cfg::B_BYTES + q * Cfg::B_BOX, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0,
+                                 st * Cfg::KWS + q, 0);
+              } else
                 tma_load_3d_if(issue, smem_b + s * Cfg::B_BYTES, &maps.b[src][pass == 2], &b_full[s], kc * KC, n0,
                                src == 0 ? st * Cfg::TPB : 0);
               ++bi;
@@ -234,27 +247,32 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
                     // rows).  Halo plane hq feeds output planes hq-kd; accumulators sit in DESCENDING plane order in
                     // TMEM, so one MMA with N = nkd*BN columns starting at plane (hq-kdmin) covers them: N = 32 costs
                     // 40-46 cycles, N = 96 only 56, i.e. 6 MMAs replace 12 per (kh,kw,k16) at TD = 4.
-                    static_assert(Cfg::TPB == 3, "stacked stages hold 3 taps");
+                    static_assert(Cfg::TPB == 3, "stacked boxes hold 3 taps");
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                      if (k == 0 && first) {
-                        // very first K step of the tile: unstacked, the kd = 0 MMA of every plane overwrites
+                    for (int q = 0; q < Cfg::KWS; ++q) {   // KWS = 3: the stage holds the kw = 0,1,2 boxes of one kh
+                      const uint32_t a_q = a_base + ((q * Cfg::RB) >> 4);
+                      const uint32_t b_q = b_lo0 + ((q * Cfg::B_BOX) >> 4);
 #pragma unroll
-                        for (int dpl = 0; dpl < TD; ++dpl) {
+                      for (int k = 0; k < KC / 16; ++k) {
+                        if (q == 0 && k == 0 && first) {
+                          // very first K step of the tile: unstacked, the kd = 0 MMA of every plane overwrites
 #pragma unroll
-                          for (int kd = 0; kd < 3; ++kd)
-                            umma_bf16(acc0 + (TD - 1 - dpl) * BN, desc_from(a_base + (((dpl + kd) * 180 * Cfg::RB) >> 4), hi_a),
-                                      desc_from(b_lo0 + ((kd * Cfg::B_TAP) >> 4), hi_b), idesc, kd > 0 ? 1u : 0u);
-                        }
-                      } else {
+                          for (int dpl = 0; dpl < TD; ++dpl) {
 #pragma unroll
-                        for (int hq = 0; hq < TD + 2; ++hq) {
-                          const int kdmin = hq - (TD - 1) > 0 ? hq - (TD - 1) : 0;
-                          const int kdmax = hq < 2 ? hq : 2;
-                          const int nkd = kdmax - kdmin + 1;
-                          const uint32_t idn = nkd == 1 ? idesc : nkd == 2 ? idesc2 : idesc3;
-                          umma_bf16(acc0 + (TD - 1 - hq + kdmin) * BN, desc_from(a_base + ((hq * 180 * Cfg::RB + k * 32) >> 4), hi_a),
-                                    desc_from(b_lo0 + ((kdmin * Cfg::B_TAP + k * 32) >> 4), hi_b), idn, 1u);
+                            for (int kd = 0; kd < 3; ++kd)
+                              umma_bf16(acc0 + (TD - 1 - dpl) * BN, desc_from(a_q + (((dpl + kd) * 180 * Cfg::RB) >> 4), hi_a),
+                                        desc_from(b_q + ((kd * Cfg::B_TAP) >> 4), hi_b), idesc, kd > 0 ? 1u : 0u);
+                          }
+                        } else {
+#pragma unroll
+                          for (int hq = 0; hq < TD + 2; ++hq) {
+                            const int kdmin = hq - (TD - 1) > 0 ? hq - (TD - 1) : 0;
+                            const int kdmax = hq < 2 ? hq : 2;
+                            const int nkd = kdmax - kdmin + 1;
+                            const uint32_t idn = nkd == 1 ? idesc : nkd == 2 ? idesc2 : idesc3;
+                            umma_bf16(acc0 + (TD - 1 - hq + kdmin) * BN, desc_from(a_q + ((hq * 180 * Cfg::RB + k * 32) >> 4), hi_a),
+                                      desc_from(b_q + ((kdmin * Cfg::B_TAP + k * 32) >> 4), hi_b), idn, 1u);
+                          }
                         }
                       }
                     }
@@ -274,12 +292,16 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
                 first = 0;
               }
               if (++bs == NB) { bs = 0; bph ^= 1; }
-              // next tap: kw fastest, then kh, (then kd for unstacked stages)
-              a_off += Cfg::RB >> 4;
-              if (++kw == 3) {
-                kw = 0;
-                a_off += (7 * Cfg::RB) >> 4;
-                if (++kh == 3) { kh = 0; a_off += (15 * 10 * Cfg::RB) >> 4; }
+              if constexpr (Cfg::KWS == 3) {
+                a_off += (10 * Cfg::RB) >> 4;   // next stage = next kh: one halo row of 10 voxels further
+              } else {
+                // next tap: kw fastest, then kh, (then kd for unstacked stages)
+                a_off += Cfg::RB >> 4;
+                if (++kw == 3) {
+                  kw = 0;
+                  a_off += (7 * Cfg::RB) >> 4;
+                  if (++kh == 3) { kh = 0; a_off += (15 * 10 * Cfg::RB) >> 4; }
+                }
               }
             }
             sidx += STAGES0;
@@ -595,7 +617,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
   // staging buffers: column-split groups share a ring of 2; plane-split groups own 2 each if they fit, else 1 each
-  h.nout = Cfg::COLSPLIT ? 2 : (rem - 4 * out_buf >= 4 * Cfg::B_BYTES) ? 4 : 2;
+  h.nout = Cfg::COLSPLIT ? 2 : (rem - 4 * out_buf >= 4 * Cfg::B_BOX_BYTES && rem - 4 * out_buf >= 2 * Cfg::B_BYTES) ? 4 : 2;
   if (const char* e = getenv("B200UNET_HALO_NOUT")) {   // tuning override
     const int v = atoi(e);
     if (Cfg::COLSPLIT) { if (v == 1 || v == 2) h.nout = v; }   // shared ring of 1 or 2
@@ -641,7 +663,11 @@ bool conv_halo_eligible(const ConvOp& op) {
 static bool halo_fits(int KC, int BN, int TD, bool split) {
   const int halo = (180 * (TD + 2) * KC * 2 + 1023) / 1024 * 1024;
   const int tpb = BN <= 64 ? 3 : 1;
-  const int bbytes = (tpb * BN * KC * 2 + 1023) / 1024 * 1024;
+  int box = tpb * BN * KC * 2;
+#ifndef B200_HALO_KWS1
+  if (BN <= 32 && box % 1024 == 0) box *= 3;   // HaloCfg::KWS
+#endif
+  const int bbytes = (box + 1023) / 1024 * 1024;
   const int aux = 1024 + 8 * BN * 8 + BN * 16;
   const int out_buf = 128 * BN * 2 * (split ? 2 : 1);
   return 232448 - 1024 - aux - 2 * halo - 2 * out_buf >= 2 * bbytes;

@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+# B200UNET_LIB: load a differently-built copy of the library (A/B runs of compile-time kernel variants: tools/gpu_experiments.sh)
+LIB_PATH = os.environ.get("B200UNET_LIB") or os.path.join(_HERE, "libb200unet.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "b200unet.h")
 
@@ -45,6 +46,8 @@ class NetDesc(C.Structure):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile libb200unet.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if os.environ.get("B200UNET_LIB"):
+        return LIB_PATH                       # an explicitly chosen variant is never rebuilt behind the caller's back
     if os.path.exists(LIB_PATH) and not force:
         src_m = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)
                     if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile")
