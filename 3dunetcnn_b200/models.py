@@ -109,8 +109,8 @@ class _UNetFunction(torch.autograd.Function):
     """forward+backward of the whole network as two library calls."""
 
     @staticmethod
-    def forward(ctx, model, x, drop, *params):
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, model, x, drop, need_bwd, *params):
+        # need_bwd is decided by the caller: inside Function.forward autograd's grad mode is always off
         plan = model._plan_for(x, inference_only=not need_bwd)
         n, _, d, h, w = x.shape
         logits = torch.empty((n, model.n_outputs, d, h, w), dtype=torch.float32, device=x.device)
@@ -149,8 +149,8 @@ class _UNetFunction(torch.autograd.Function):
                                                        plan.workspace.data_ptr(), _lib.stream_ptr()), "plan_backward")
         model.launches_last_backward = plan.last_launches()
         if direct:                      # flat-bucket mode: the gradients already sit in the parameters' .grad views
-            return (None, None, None) + (None,) * len(params)
-        return (None, None, None) + tuple(grads)
+            return (None, None, None, None) + (None,) * len(params)
+        return (None, None, None, None) + tuple(grads)
 
 
 class _PlanModel(nn.Module):
@@ -248,6 +248,11 @@ class _PlanModel(nn.Module):
         return [torch.empty_like(p) for p in params], False
 
     _overwrite_grads = False   # set by train.GraphedTrainStep while it owns the step
+
+    @staticmethod
+    def _needs_backward(params) -> bool:
+        """training plan (activations kept) iff autograd will ask for a backward; otherwise the forward-only plan"""
+        return bool(torch.is_grad_enabled() and any(p.requires_grad for p in params))
 
     def _check_input(self, x: torch.Tensor, n_in: int) -> torch.Tensor:
         if not isinstance(x, torch.Tensor) or x.dim() != 5:
@@ -406,7 +411,7 @@ class UNet3D(_PlanModel):
             else:
                 keep = (torch.rand((xp.shape[0], self.base_width), device=xp.device) >= self.dropout_p)
                 drop = keep.float() / (1.0 - self.dropout_p)
-        return _UNetFunction.apply(self, xp, drop, *params)
+        return _UNetFunction.apply(self, xp, drop, self._needs_backward(params), *params)
 
 
 class AutocastUNet(UNet3D):
@@ -535,7 +540,8 @@ class DynUNet(_PlanModel):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         xp = self._check_input(x, self.in_channels)
-        return _UNetFunction.apply(self, xp, None, *self.ordered_parameters())
+        params = self.ordered_parameters()
+        return _UNetFunction.apply(self, xp, None, self._needs_backward(params), *params)
 
 
 _MODELS = {"UNet3D": UNet3D, "AutocastUNet": AutocastUNet, "AutoImplantUNet": AutoImplantUNet,

@@ -192,3 +192,58 @@ def test_conv_halo_incremental_tap_offsets(stacked):
             if kh == 3:
                 kh = 0
                 a_off += 15 * 10 * rb
+
+
+def test_conv_halo_kw_grouped_stage_offsets():
+    """BN <= 32: a weight stage holds the kw = 0,1,2 boxes of one kh (HaloCfg::KWS = 3).  Stage st = kh advances the A offset by
+    one halo row (10 voxels); box q of the stage is kw = q (+1 voxel) and sits q boxes into the stage; the TMA box index of
+    the 4-D (Cin, Cout, khkw, kd) weight view is st * 3 + q."""
+    rb = 4
+    b_box = 3 * 2048                                           # three kd tiles of a 32 x 32 tap
+    a_off = 0
+    taps = set()
+    for st in range(3):
+        for q in range(3):
+            khkw = st * 3 + q
+            assert khkw == st * 3 + q and khkw // 3 == st and khkw % 3 == q
+            a_q = a_off + q * rb
+            for kd in range(3):
+                assert a_q + kd * 180 * rb == ((kd * 18 + st) * 10 + q) * rb
+                taps.add((kd, st, q, q * b_box + kd * 2048))    # B operand offset inside the stage
+        a_off += 10 * rb
+    assert len(taps) == 27 and len({t[3] for t in taps}) == 9   # 9 distinct tile offsets per stage x 3 stages
+
+
+def test_stride2_dgrad_parity_class_tap_lists():
+    """cls_mode 1 (igemm_conv.cu): dx[i] = sum_o sum_k dy[o] w[k] [2o + k - 1 == i].  With the flipped pack Wd[k'] = w[2 - k'],
+    class parity p lists (k', delta) with source index j + delta for output 2j + p; the 8 classes hold 27 tap products."""
+    import itertools
+    for p in (0, 1):
+        lst = [(k, 1 if k == 2 else 0) for k in range(3) if (k != 1 if p else k == 1)]
+        for j in range(1, 5):
+            i = 2 * j + p
+            direct = sorted((o, k) for o in range(0, 8) for k in range(3) if 2 * o + k - 1 == i)
+            via = sorted((j + delta, 2 - kp) for kp, delta in lst)      # (dy index, un-flipped w index)
+            assert direct == via
+    total = sum(len([k for k in range(3) if (k != 1 if pd else k == 1)]) * len([k for k in range(3) if (k != 1 if ph else k == 1)]) *
+                len([k for k in range(3) if (k != 1 if pw else k == 1)]) for pd, ph, pw in itertools.product((0, 1), repeat=3))
+    assert total == 27
+
+
+def test_transposed_conv_k2s2_roles():
+    """ConvTranspose3d(kernel = stride = 2): U[2j + p] = sum_ci X[j] W[ci][co][p] -> class p uses tap p (cls_mode 2); its data
+    gradient is the unpadded kernel-2 stride-2 convolution of dU and its weight gradient the same convolution's filter
+    gradient with roles swapped (checked numerically against torch in 1-D per axis)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 5, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(3, 4, 2, dtype=torch.float64, requires_grad=True)
+    u = F.conv_transpose1d(x, w, stride=2)
+    for p in (0, 1):
+        assert torch.allclose(u[0, :, p::2], torch.einsum("cj,co->oj", x[0], w[:, :, p]))
+    du = torch.randn_like(u)
+    u.backward(du)
+    dx = F.conv1d(du, w.permute(0, 1, 2).reshape(3, 4, 2), stride=2)          # V[p][ci][co] = w[ci][co][p], no padding
+    assert torch.allclose(dx, x.grad)
+    dw = torch.stack([torch.einsum("cj,oj->co", x[0].detach(), du[0, :, t::2]) for t in (0, 1)], dim=-1)
+    assert torch.allclose(dw, w.grad)
