@@ -25,8 +25,26 @@ def _worker(rank, world, port, q):
     for p in params[:2]:
         p.grad = torch.full_like(p, float(rank + 1))
     sync()
+    # flat-gradient mode: the gradients are views of one persistent bucket which is all-reduced in place (no copies)
+    class Bucketed:
+        def __init__(self, ps):
+            self.bucket = torch.zeros(sum(p.numel() for p in ps))
+            off = 0
+            for p in ps:
+                p.grad = self.bucket[off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+        def flat_gradient_bucket(self):
+            return self.bucket
+    qs = [torch.nn.Parameter(torch.zeros(4, 2)), torch.nn.Parameter(torch.zeros(3))]
+    model = Bucketed(qs)
+    model.bucket.fill_(float(10 * (rank + 1)))
+    ptrs = [q_.grad.data_ptr() for q_ in qs]
+    sync2 = par.GradAllReduce(qs, model=model)
+    sync2()
+    assert [q_.grad.data_ptr() for q_ in qs] == ptrs and sync2.flat is None      # reduced in place, no staging buffer
     out = {"p0": params[0].detach().clone(), "g0": params[0].grad.clone(), "g1": params[1].grad.clone(),
-           "shard": list(par.shard_batch(7, rank, world))}
+           "shard": list(par.shard_batch(7, rank, world)), "bucket": model.bucket.clone()}
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -48,6 +66,8 @@ def test_grad_allreduce_and_sharding_world2():
         assert torch.allclose(res[r]["g0"], torch.full((5, 3), 1.5))      # mean of 1 and 2
         assert torch.allclose(res[r]["g1"], torch.full((7,), 1.5))
     assert res[0]["shard"] == [0, 1, 2, 3] and res[1]["shard"] == [4, 5, 6]
+    for r in (0, 1):
+        assert torch.allclose(res[r]["bucket"], torch.full((11,), 15.0))  # mean of 10 and 20, in the bucket itself
 
 
 def test_single_process_is_a_noop():
