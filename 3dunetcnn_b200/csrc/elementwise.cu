@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __
   if constexpr (FUSED) {
     // one global fp64 load pair per thread, the group sums then come from shared memory (a per-thread loop over the
     // group's channels in global memory serialised up to 64 L2 latencies in front of every block)
-    __shared__ float2 s_ab[512];
-    __shared__ double s_st[512][2];
+    __shared__ float2 s_ab[1024];
+    __shared__ double s_st[1024][2];
     for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
       s_st[c][0] = c < f.C ? f.stats[((long long)n * x.C + c) * 2 + 0] : 0.0;
       s_st[c][1] = c < f.C ? f.stats[((long long)n * x.C + c) * 2 + 1] : 0.0;
@@ -300,7 +300,7 @@ static int launch_gn_apply_impl(const Act& x, const Act& y, const float* coef, f
   const long long cap = (148LL * 8 + x.N - 1) / x.N;
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   if (fin) {
-    B200_REQUIRE(x.C <= 512, E_UNSUPPORTED, "gn_apply: fused finalize supports C <= 512 (got %d)", x.C);
+    B200_REQUIRE(x.C <= 1024, E_UNSUPPORTED, "gn_apply: fused finalize supports C <= 1024 (got %d)", x.C);
     k_gn_apply<true><<<dim3(blocks, x.N), threads, 0, st>>>(x, y, nullptr, slope, *fin);
   } else {
     GnFin none;
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __r
   const int vper = blockDim.x / c8n;
   float ka[8], ke[8], kf[8], ks[8];
   if constexpr (FUSED) {
-    __shared__ float2 s_ef[512];
-    __shared__ double s_bs[512][2];   // gamma-weighted backward statistics of every channel of this sample
+    __shared__ float2 s_ef[1024];
+    __shared__ double s_bs[1024][2];   // gamma-weighted backward statistics of every channel of this sample
     for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
       const double ga = (c < f.C && f.gamma) ? (double)f.gamma[c] : 1.0;
       s_bs[c][0] = c < f.C ? ga * f.bstats[((long long)n * x.C + c) * 2 + 0] : 0.0;
@@ -510,7 +510,7 @@ static int launch_gn_bwd_impl(const Act& dz, const Act& x, const float* coef, co
   const long long cap = (148LL * 8 + x.N - 1) / x.N;
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   if (fin) {
-    B200_REQUIRE(x.C <= 512, E_UNSUPPORTED, "gn_bwd: fused finalize supports C <= 512 (got %d)", x.C);
+    B200_REQUIRE(x.C <= 1024, E_UNSUPPORTED, "gn_bwd: fused finalize supports C <= 1024 (got %d)", x.C);
     k_gn_bwd<true><<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef), nullptr,
                                                           add1 ? *add1 : none, add2 ? *add2 : none, dx, scale, *fin);
   } else {
