@@ -26,7 +26,7 @@ namespace b200 {
 
 // NI = number of MMA-issuing warps (1, or 2 = experimental: each issuer accumulates its stages into its OWN accumulator
 // set and the epilogue adds the two; BN <= 32 only, enabled with B200UNET_HALO_ISSUERS=2)
-template <int KC, int BN, int TD, int NI = 1>
+template <int KC, int BN, int TD, int NI = 1, int KW = 1>
 struct HaloCfg {
   static constexpr int RB = KC * 2;                         // bytes per voxel row of the halo
   static constexpr int HALO_ROWS = 180 * (TD + 2);          // 10 x 18 x (TD+2)
@@ -37,14 +37,12 @@ struct HaloCfg {
   static constexpr int B_TAP = BN * KC * 2;                 // bytes of one tap's weight tile
   static constexpr int B_BOX = TPB * B_TAP;                 // bytes of one weight TMA box
   static constexpr int B_BOX_BYTES = (B_BOX + 1023) / 1024 * 1024;
-#ifdef B200_HALO_KWS1
-  static constexpr int KWS = 1;
-#else
-  // (kh,kw) boxes per weight stage.  BN <= 32: a stage holds the three kw boxes of one kh (36 instead of 12 MMAs between
-  // two stage hand-backs: the wait / fence / descriptor set-up of a hand-back cannot overlap the MMAs of the same issuing
-  // thread, ~150 cycles each -- tools/umma_rate.py: 76 cycles per MMA at 12 per stage vs 64 back to back)
-  static constexpr int KWS = (BN <= 32 && B_BOX % 1024 == 0) ? 3 : 1;
-#endif
+  // (kh,kw) boxes per weight stage (template parameter KW, chosen per launch by launch_conv_halo).  KW = 3: a stage holds the
+  // three kw boxes of one kh: 36 instead of 12 MMAs between two stage hand-backs (the wait / fence / descriptor set-up of a
+  // hand-back cannot overlap the MMAs of the same issuing thread, ~150 cycles each -- tools/umma_rate.py: 76 cycles per MMA
+  // at 12 per stage vs 64 back to back).  Needs 1024-byte multiples per box (TMA destination / UMMA descriptor alignment).
+  static constexpr int KWS = KW;
+  static_assert(KW == 1 || (KW == 3 && BN <= 32 && B_BOX % 1024 == 0), "three-box stages: BN <= 32, 1 KB aligned boxes");
   static constexpr int B_TX = KWS * B_BOX;
   static constexpr int B_BYTES = (B_TX + 1023) / 1024 * 1024;
   static constexpr int NB_MAX = 24;
@@ -83,10 +81,10 @@ struct HaloArgs {
 #define HALO_STAMP(role, slot) \
   do { if (hp.dbg && blockIdx.x == 0 && ti < 32 && lane == 0) hp.dbg[((role) * 32 + ti) * 4 + (slot)] = clock64(); } while (0)
 
-template <int KC, int BN, int TD, int NI = 1>
+template <int KC, int BN, int TD, int NI = 1, int KW = 1>
 __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __grid_constant__ ConvMaps maps, const ConvArgs p,
                                                                       const HaloArgs hp) {
-  using Cfg = HaloCfg<KC, BN, TD, NI>;
+  using Cfg = HaloCfg<KC, BN, TD, NI, KW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int out_buf_bytes = Cfg::OUT_TILE * (hp.split ? 2 : 1);
@@ -427,6 +425,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     };
 
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
+      EPI_STAMP(40);
       int t = tile;
       const int nt = t % hp.ntiles; t /= hp.ntiles;
       const int wt = t % p.tiles_w; t /= p.tiles_w;
@@ -455,14 +454,18 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       const long long vox0 = (((long long)n * p.Do + d0) * p.Ho + h) * p.Wo + w;   // plane dpl: + dpl * Ho * Wo
       const long long plane = (long long)p.Ho * p.Wo;
       const int dpl0 = COLS ? 0 : grp;
+      EPI_STAMP(41);
       load_side(vox0 + dpl0 * plane, n0, 0, valid_wh && (d0 + dpl0 < p.Do) && dpl0 < TD);   // lands while the MMAs still run
+      EPI_STAMP(42);
       for (int dpl = dpl0 + pstep; dpl < TD; dpl += pstep)     // the later planes' rows -> L2
         conv_epilogue_prefetch(p, n0 + jb * 16, NJ * 16, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
+      EPI_STAMP(43);
       const uint32_t as = ti % Cfg::NACC;
       if (warp == 2) HALO_STAMP(2, 0);
       mbar_wait(&acc_full[as], (ti / Cfg::NACC) & 1);
       tc_fence_after();
       if (warp == 2) HALO_STAMP(2, 1);
+      EPI_STAMP(44);
 #pragma unroll 1
       for (int dpl = dpl0; dpl < TD; dpl += pstep, ++oi) {
         const int d = d0 + dpl;
@@ -595,6 +598,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);      // accumulator set drained: MMA may overwrite it
+      EPI_STAMP(45);
       if (warp == 2) HALO_STAMP(2, 2);
       if (!RUN && want_stats) flush_smem(n, n0);
       if (warp == 2) HALO_STAMP(2, 3);
@@ -610,9 +614,9 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int KC, int BN, int TD, int NI = 1>
+template <int KC, int BN, int TD, int NI = 1, int KW = 1>
 static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, int grid, cudaStream_t st) {
-  using Cfg = HaloCfg<KC, BN, TD, NI>;
+  using Cfg = HaloCfg<KC, BN, TD, NI, KW>;
   // shared-memory carve-up: 2 halo buffers | nout output staging buffers | weight ring | aux
   const int out_buf = Cfg::OUT_TILE * (h.split ? 2 : 1);
   const int rem = Cfg::BUDGET - Cfg::AUX_BYTES - Cfg::NHALO * Cfg::HALO_BYTES;
@@ -632,10 +636,10 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD, NI, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD, NI><<<grid, NI == 2 ? 384 : 352, smem_bytes, st>>>(maps, a, h);
+  k_conv_halo<KC, BN, TD, NI, KW><<<grid, NI == 2 ? 384 : 352, smem_bytes, st>>>(maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -660,13 +664,10 @@ bool conv_halo_eligible(const ConvOp& op) {
 }
 
 // does (KC, BN, TD, split) fit the shared-memory budget with at least a 2-deep weight ring and 1 staging buffer?
-static bool halo_fits(int KC, int BN, int TD, bool split) {
+static bool halo_fits(int KC, int BN, int TD, bool split, int kws = 1) {
   const int halo = (180 * (TD + 2) * KC * 2 + 1023) / 1024 * 1024;
   const int tpb = BN <= 64 ? 3 : 1;
-  int box = tpb * BN * KC * 2;
-#ifndef B200_HALO_KWS1
-  if (BN <= 32 && box % 1024 == 0) box *= 3;   // HaloCfg::KWS
-#endif
+  const int box = tpb * BN * KC * 2 * kws;
   const int bbytes = (box + 1023) / 1024 * 1024;
   const int aux = 1024 + 8 * BN * 8 + BN * 16;
   const int out_buf = 128 * BN * 2 * (split ? 2 : 1);
@@ -788,17 +789,28 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);
   const int grid = h.tiles_total < num_sms ? h.tiles_total : num_sms;
-  // experimental: two issuing warps with private accumulator sets (BN <= 32, at least two weight stages per tile)
-  static const bool two_issuers = getenv("B200UNET_HALO_ISSUERS") && atoi(getenv("B200UNET_HALO_ISSUERS")) == 2;
-  const int stages_per_tile = (a.kchunks[0] * (BN <= 64 ? 9 : 27) + (a.ntaps[1] ? a.kchunks[1] : 0)) * a.npass;
-  if (two_issuers && BN <= 32 && stages_per_tile >= 2) {
-#define B200_HALO_CASE2(kc, bn, td) \
-  if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td, 2>(maps, a, h, grid, st);
-    B200_HALO_CASE2(16, 16, 4) B200_HALO_CASE2(16, 16, 2) B200_HALO_CASE2(16, 16, 1)
-    B200_HALO_CASE2(16, 32, 4) B200_HALO_CASE2(16, 32, 2) B200_HALO_CASE2(16, 32, 1)
-    B200_HALO_CASE2(32, 16, 4) B200_HALO_CASE2(32, 16, 2) B200_HALO_CASE2(32, 16, 1)
-    B200_HALO_CASE2(32, 32, 4) B200_HALO_CASE2(32, 32, 2) B200_HALO_CASE2(32, 32, 1)
-#undef B200_HALO_CASE2
+  // Three-box weight stages (KW = 3) where they measured faster on B200 (profiles/r02_convbench*.log, batch-2 128^3 layers):
+  //   64->32 all epilogues -15 %, 32->32 with a plain / statistics epilogue -10 %, 32->8 GroupNorm-backward epilogue -17 %;
+  //   but 32->32 with a side input (residual, GroupNorm-backward) +12..25 % and 8->32 +6 % -> those keep one box per stage.
+  // (The round-1 experiment with two issuing warps and private accumulator sets, NI = 2, ran correctly but slower than
+  //  either variant -- 0.38 vs 0.30 ms on 32->32+residual -- and is no longer instantiated.)
+  const bool side_input = op.res != nullptr || op.mode == 1;
+  int kws = 1;
+  if (BN <= 32 && (tpb * BN * KC * 2) % 1024 == 0 && KC == 32) {
+    if (a.kchunks[0] >= 2 || BN < 32 || !side_input) kws = 3;
+  }
+  if (const char* e = getenv("B200UNET_HALO_KWS")) {   // tuning override (1 or 3)
+    const int v = atoi(e);
+    if (v == 1 || (v == 3 && BN <= 32 && (tpb * BN * KC * 2) % 1024 == 0)) kws = v;
+  }
+  if (kws == 3 && !halo_fits(KC, BN, TD, split, 3)) kws = 1;
+  if (kws == 3) {
+#define B200_HALO_CASE3(kc, bn, td) \
+  if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td, 1, 3>(maps, a, h, grid, st);
+    B200_HALO_CASE3(16, 32, 4) B200_HALO_CASE3(16, 32, 2) B200_HALO_CASE3(16, 32, 1)
+    B200_HALO_CASE3(32, 16, 4) B200_HALO_CASE3(32, 16, 2) B200_HALO_CASE3(32, 16, 1)
+    B200_HALO_CASE3(32, 32, 4) B200_HALO_CASE3(32, 32, 2) B200_HALO_CASE3(32, 32, 1)
+#undef B200_HALO_CASE3
   }
 #define B200_HALO_CASE(kc, bn, td) \
   if (KC == kc && BN == bn && TD == td) return launch_halo_cfg<kc, bn, td>(maps, a, h, grid, st);

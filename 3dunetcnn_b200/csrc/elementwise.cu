@@ -886,42 +886,25 @@ __global__ void k_head_bwd(Act x, const float* __restrict__ w, const float* __re
   for (int o = 0; o < NO; ++o)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[o][j] = sw[o * x.C + c8 * 8 + j];
-  // UF voxels in flight per thread (all loads of an iteration are issued before the first FMA): with one voxel per
-  // iteration the kernel ran at ~40% of the HBM rate (register-limited occupancy, one 16-byte load in flight per thread)
-  constexpr int UF = 4;
-  const long long tstride = (long long)gridDim.x * blockDim.x;
-  for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += UF * tstride) {
-    float g[UF][NO], u[UF][8];
-    bool ok[UF];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / c8n;
+    const int n = (int)(v / S);
+    const long long s = v % S;
+    float g[NO];
 #pragma unroll
-    for (int q = 0; q < UF; ++q) {
-      const long long t = t0 + q * tstride;
-      ok[q] = t < total;
-      if (ok[q]) {
-        const long long v = t / c8n;
-        const int n = (int)(v / S);
-        const long long s = v % S;
+    for (int o = 0; o < NO; ++o) g[o] = __ldg(dlogits + ((long long)n * NO + o) * S + s);
+    float u[8], d[8];
+    load8(x.hi, x.lo, v * x.ld + c8 * 8, u);
 #pragma unroll
-        for (int o = 0; o < NO; ++o) g[q][o] = __ldg(dlogits + ((long long)n * NO + o) * S + s);
-        load8(x.hi, x.lo, v * x.ld + c8 * 8, u[q]);
+    for (int j = 0; j < 8; ++j) d[j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = fmaf(g[o], wr[o][j], d[j]);
+        pdw[o][j] = fmaf(g[o], u[j], pdw[o][j]);
       }
-    }
-#pragma unroll
-    for (int q = 0; q < UF; ++q) {
-      if (!ok[q]) continue;
-      const long long v = (t0 + q * tstride) / c8n;
-      float d[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = 0.f;
-#pragma unroll
-      for (int o = 0; o < NO; ++o)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          d[j] = fmaf(g[q][o], wr[o][j], d[j]);
-          pdw[o][j] = fmaf(g[q][o], u[q][j], pdw[o][j]);
-        }
-      store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
-    }
+    store8(dx.hi, dx.lo, v * dx.ld + c8 * 8, d);
   }
   // Block reduction in a FIXED order (no floating-point atomics): per-thread partials -> shared memory -> thread i sums the
   // threads that own channel i's chunk (t = c8, c8 + c8n, ...) -> this block's slot of `part`; k_sum_slots then adds the

@@ -49,14 +49,11 @@ __device__ __forceinline__ void st8(bf16* hi, bf16* lo, long long off, const flo
 constexpr int PT = 16;        // tile edge along co and ci
 constexpr int PTT = 29;       // padded tap pitch (27 taps; odd pitch: conflict-free column reads)
 
-__global__ void __launch_bounds__(256) k_pack_all_tiled(PtrTable params, const PackJob* __restrict__ jobs, uint8_t* __restrict__ ws,
-                                                       int split) {
-  __shared__ float tile[PT][PT + 1][PTT];   // odd (ci) pitch: both store orders read (nearly) conflict-free
-  const PackJob j = jobs[blockIdx.y];
-  const float* __restrict__ w = reinterpret_cast<const float*>(params.p[j.pidx]);
-  bf16* hi = reinterpret_cast<bf16*>(ws + j.off_hi);
-  bf16* lo = split ? reinterpret_cast<bf16*>(ws + j.off_lo) : nullptr;
-  const int T = j.T;
+// TC: compile-time tap count (27, 8, 1) so that the index divisions fold into multiplies; 0 = runtime j.T
+template <int TC>
+__device__ __forceinline__ void pack_job_tiled(float (&tile)[PT][PT + 1][PTT], const PackJob& j, const float* __restrict__ w,
+                                               bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const int T = TC ? TC : j.T;
   const bool tsrc = j.mode >= 2;                       // ConvTranspose3d weight [Ci][Co][T]
   const bool flip = j.mode == 1 || j.mode == 2;
   const bool co_inner = j.mode == 1 || j.mode == 3;    // data-gradient layout [T][Cip][Cop]
@@ -94,13 +91,23 @@ __global__ void __launch_bounds__(256) k_pack_all_tiled(PtrTable params, const P
   }
 }
 
-__global__ void __launch_bounds__(256) k_unpack_all_tiled(PtrTable grads, const PackJob* __restrict__ jobs,
-                                                         const uint8_t* __restrict__ ws) {
-  __shared__ float tile[PT][PT + 1][PTT];
+__global__ void __launch_bounds__(256) k_pack_all_tiled(PtrTable params, const PackJob* __restrict__ jobs, uint8_t* __restrict__ ws,
+                                                       int split) {
+  __shared__ float tile[PT][PT + 1][PTT];   // odd (ci) pitch: both store orders read (nearly) conflict-free
   const PackJob j = jobs[blockIdx.y];
-  float* __restrict__ out = const_cast<float*>(reinterpret_cast<const float*>(grads.p[j.pidx]));
-  const float* __restrict__ g = reinterpret_cast<const float*>(ws + j.off_hi);   // fp32 accumulator [T][Cip][Cop]
-  const int T = j.T;
+  const float* __restrict__ w = reinterpret_cast<const float*>(params.p[j.pidx]);
+  bf16* hi = reinterpret_cast<bf16*>(ws + j.off_hi);
+  bf16* lo = split ? reinterpret_cast<bf16*>(ws + j.off_lo) : nullptr;
+  if (j.T == 27) pack_job_tiled<27>(tile, j, w, hi, lo);
+  else if (j.T == 1) pack_job_tiled<1>(tile, j, w, hi, lo);
+  else if (j.T == 8) pack_job_tiled<8>(tile, j, w, hi, lo);
+  else pack_job_tiled<0>(tile, j, w, hi, lo);
+}
+
+template <int TC>
+__device__ __forceinline__ void unpack_job_tiled(float (&tile)[PT][PT + 1][PTT], const PackJob& j, const float* __restrict__ g,
+                                                 float* __restrict__ out) {
+  const int T = TC ? TC : j.T;
   const bool tdst = j.mode == 2;   // ConvTranspose3d gradient layout [Ci][Co][T], taps flipped back
   const int nco = (j.Co + PT - 1) / PT, nci = (j.Ci + PT - 1) / PT;
   for (int tl = blockIdx.x; tl < nco * nci; tl += gridDim.x) {
@@ -124,6 +131,18 @@ __global__ void __launch_bounds__(256) k_unpack_all_tiled(PtrTable grads, const 
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_all_tiled(PtrTable grads, const PackJob* __restrict__ jobs,
+                                                         const uint8_t* __restrict__ ws) {
+  __shared__ float tile[PT][PT + 1][PTT];
+  const PackJob j = jobs[blockIdx.y];
+  float* __restrict__ out = const_cast<float*>(reinterpret_cast<const float*>(grads.p[j.pidx]));
+  const float* __restrict__ g = reinterpret_cast<const float*>(ws + j.off_hi);   // fp32 accumulator [T][Cip][Cop]
+  if (j.T == 27) unpack_job_tiled<27>(tile, j, g, out);
+  else if (j.T == 1) unpack_job_tiled<1>(tile, j, g, out);
+  else if (j.T == 8) unpack_job_tiled<8>(tile, j, g, out);
+  else unpack_job_tiled<0>(tile, j, g, out);
 }
 
 int launch_pack_all_tiled(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st) {
@@ -225,7 +244,12 @@ __global__ void __launch_bounds__(UD * UH * UW * (UCT / 8)) k_upsample2x_bwd_til
   st8(dx.hi, dx.lo, ((((long long)n * dx.D + d) * dx.H + h) * dx.W + w) * dx.ld + c0 + ch * 8, o);
 }
 
-bool use_tiled_upsample_bwd() { return !old_small_ops(); }
+bool use_tiled_upsample_bwd() {
+  // measured on B200 (profiles/r02_layer_times_*.csv): 0.316 ms tiled vs 0.293 ms for the L1-cached gather version at
+  // 32ch 64^3 -> kept as an opt-in experiment
+  static const bool v = getenv("B200UNET_TILED_UPSAMPLE_BWD") != nullptr;
+  return v;
+}
 
 int launch_upsample2x_bwd_tiled(const Act& dy, const Act& dx, cudaStream_t st) {
   B200_REQUIRE(dx.C % 8 == 0 && dy.C == dx.C, E_INVALID, "upsample_bwd: channel mismatch");
@@ -271,17 +295,53 @@ __global__ void __launch_bounds__(256) k_wgrad_1x1_narrow(Act a, Act dy, float* 
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const long long total = a.voxels();
   const long long stride = (long long)gridDim.x * vper;
-  for (long long v = (long long)blockIdx.x * vper + vslot; v < total; v += stride) {
-    float g[8];
-    ld8(dy.hi, dy.lo, v * dy.ld + cy * 8, g);
+  // UF voxels in flight per thread: all loads of an iteration are issued before the first FMA (one voxel per iteration left
+  // the kernel latency-bound at ~1.3 TB/s)
+  constexpr int UF = 4;
+  for (long long v0 = (long long)blockIdx.x * vper + vslot; v0 < total; v0 += UF * stride) {
+    uint4 gq[UF], xq[UF][CI8];
 #pragma unroll
-    for (int q = 0; q < CI8; ++q) {
-      float x[8];
-      ld8(a.hi, a.lo, v * a.ld + q * 8, x);
+    for (int q = 0; q < UF; ++q) {
+      const long long v = v0 + q * stride;
+      if (v < total) {
+        gq[q] = *reinterpret_cast<const uint4*>(dy.hi + v * dy.ld + cy * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int c = 0; c < CI8; ++c) xq[q][c] = *reinterpret_cast<const uint4*>(a.hi + v * a.ld + c * 8);
+      } else {
+        gq[q] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[q * 8 + i][j] = fmaf(x[i], g[j], acc[q * 8 + i][j]);
+        for (int c = 0; c < CI8; ++c) xq[q][c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UF; ++q) {
+      const long long v = v0 + q * stride;
+      float g[8];
+      g[0] = bf16_lo_to_f(gq[q].x); g[1] = bf16_hi_to_f(gq[q].x); g[2] = bf16_lo_to_f(gq[q].y); g[3] = bf16_hi_to_f(gq[q].y);
+      g[4] = bf16_lo_to_f(gq[q].z); g[5] = bf16_hi_to_f(gq[q].z); g[6] = bf16_lo_to_f(gq[q].w); g[7] = bf16_hi_to_f(gq[q].w);
+      if (dy.lo && v < total) {
+        float gl[8];
+        ld8(dy.lo, nullptr, v * dy.ld + cy * 8, gl);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += gl[j];
+      }
+#pragma unroll
+      for (int c = 0; c < CI8; ++c) {
+        float x[8];
+        const uint4 xa = xq[q][c];
+        x[0] = bf16_lo_to_f(xa.x); x[1] = bf16_hi_to_f(xa.x); x[2] = bf16_lo_to_f(xa.y); x[3] = bf16_hi_to_f(xa.y);
+        x[4] = bf16_lo_to_f(xa.z); x[5] = bf16_hi_to_f(xa.z); x[6] = bf16_lo_to_f(xa.w); x[7] = bf16_hi_to_f(xa.w);
+        if (a.lo && v < total) {
+          float xl[8];
+          ld8(a.lo, nullptr, v * a.ld + c * 8, xl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] += xl[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c * 8 + i][j] = fmaf(x[i], g[j], acc[c * 8 + i][j]);
+      }
     }
   }
   const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;   // then lanes l, l' share the chunk iff l % c8n == l' % c8n

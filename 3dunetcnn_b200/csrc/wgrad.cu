@@ -235,7 +235,13 @@ static void pick_tile_w(int Wo, int Ho, int Do, int& tw, int& th, int& td) {
 template <int CB, int BN>
 static int launch_wg(const WgradMaps& maps, const WgradArgs& a, dim3 grid, cudaStream_t st) {
   using Cfg = WgradCfg<CB, BN>;
-  B200_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  static bool attr_set[64] = {false};   // once per device: not a stream operation, keep it out of CUDA-graph captures
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_set[dev]) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (dev < 64) attr_set[dev] = true;
+  }
   k_wgrad<CB, BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;

@@ -67,7 +67,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, criterion, optimizer, images_shape, target_shape, target_dtype=torch.uint8, device=None,
-                 grad_sync=None, warmup: int = 2):
+                 grad_sync=None, warmup: int = 2, capture_error_mode: str = "thread_local"):
         self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
         device = device or next(model.parameters()).device
         self.images = torch.zeros(tuple(images_shape), dtype=torch.float32, device=device)
@@ -76,6 +76,9 @@ class GraphedTrainStep:
         self.loss = None
         self.warmup = int(warmup)
         self.device = device
+        # "thread_local": CUDA calls of OTHER threads (a DataLoader's pin-memory thread, NCCL's watchdog) do not invalidate
+        # the capture; everything this thread issues inside the capture is stream-ordered work on the capture stream
+        self.capture_error_mode = capture_error_mode
 
     def _capture(self):
         model = self.model
@@ -92,7 +95,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize(self.device)
         model._overwrite_grads = True
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
             self.loss = self.criterion(model(self.images), self.target)
             self.loss.backward()
 

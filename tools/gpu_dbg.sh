@@ -1,8 +1,21 @@
-cd /root/repo 2>/dev/null || true
+#!/bin/bash
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_prepost.py -x -q -k "graphed_train_step" 2>&1 | tail -120 > gpurun_out/r02b_graph.log
-timeout 600 python -m pytest tests/test_gpu_dynunet.py -x -q -k "1-2-filters1" 2>&1 | tail -80 > gpurun_out/r02b_dyn.log
-timeout 600 python -m pytest tests/test_gpu_prepost.py -q -k "second_forward or forward_only" 2>&1 | tail -80 > gpurun_out/r02b_misc.log
-timeout 900 python bench.py --config C5 2>gpurun_out/r02b_bench_C5.err > gpurun_out/r02b_bench_C5.json; tail -5 gpurun_out/r02b_bench_C5.err; cut -c1-600 gpurun_out/r02b_bench_C5.json
-timeout 900 python bench.py --config C2 --no-graph 2>gpurun_out/r02b_bench_C2_nograph.err > gpurun_out/r02b_bench_C2_nograph.json; tail -5 gpurun_out/r02b_bench_C2_nograph.err; cut -c1-900 gpurun_out/r02b_bench_C2_nograph.json
-tools/gpu_experiments.sh r02b
+TAG=${1:-r02c}
+timeout 600 python tools/graph_debug.py > gpurun_out/${TAG}_graph_debug.log 2>&1; cat gpurun_out/${TAG}_graph_debug.log
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/${TAG}_pytest.log; tail -12 gpurun_out/${TAG}_pytest.log
+timeout 600 python tools/layer_times.py gpurun_out/${TAG}_layer_times.csv > gpurun_out/${TAG}_layer_times.log 2>&1; head -1 gpurun_out/${TAG}_layer_times.log; tail -1 gpurun_out/${TAG}_layer_times.log
+for a in "32 32 128 plain" "32 32 128 res" "32 64 128 mode1" "64 32 128 plain"; do
+  echo "## $a" >> gpurun_out/${TAG}_halo_timeline.txt
+  timeout 120 python tools/halo_timeline.py $a >> gpurun_out/${TAG}_halo_timeline.txt 2>&1
+done
+grep "steady-state\|epilogue warp 2" gpurun_out/${TAG}_halo_timeline.txt
+for a in "32 32 128 res" "32 64 128 mode1"; do
+  tag=$(echo $a | tr ' ' '_')
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_conv_halo -s 2 -c 1 -f -o gpurun_out/${TAG}_halo_$tag python tools/halo_timeline.py $a > gpurun_out/ncu_$tag.log 2>&1
+  tail -2 gpurun_out/ncu_$tag.log
+done
+for c in C2 C3 C5; do
+  timeout 900 python bench.py --config $c 2>gpurun_out/${TAG}_bench_$c.err > gpurun_out/${TAG}_bench_$c.json
+  tail -2 gpurun_out/${TAG}_bench_$c.err; cut -c1-700 gpurun_out/${TAG}_bench_$c.json
+done

@@ -45,3 +45,6 @@ for dpl in range(4):
     v = [int(ep[dpl * 8 + i]) for i in (0, 2, 3, 4, 5, 6)]
     if v[0]:
         print("  plane %d:" % dpl, [v[i + 1] - v[i] for i in range(5)], " total", v[5] - v[0])
+top = [int(ep[40 + i]) for i in range(6)]
+if top[0]:
+    print("epilogue warp 2, tile 4: [decode+coef, load_side issue, prefetch issue, wait acc_full, drain] =", [top[i + 1] - top[i] for i in range(5)])
