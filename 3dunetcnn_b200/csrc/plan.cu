@@ -51,6 +51,7 @@ struct RunCtx {
   int launches;
   struct Prof* prof;
   const char* label;   // name of the op being launched (profiling only)
+  bool skip_pack;      // the packed bf16 weights in the workspace are current (parameters unchanged since the last forward)
 };
 
 // CAT_CONV_HALO: forward / data-gradient convolutions that run on the halo-resident kernel (conv_halo.cu); CAT_CONV_FWD and
@@ -624,7 +625,7 @@ static int build_unet3d(Plan& P) {
       B200_CHECK_CUDA(cudaStreamSynchronize(cx.st));   // `all` is a temporary; happens once per workspace
       P.jobs_uploaded_for = cx.ws;
     }
-    {
+    if (!cx.skip_pack) {
       PtrTable tbl;
       memset(&tbl, 0, sizeof(tbl));
       for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.params[i];
@@ -1008,11 +1009,13 @@ static int build_dynunet(Plan& P) {
       B200_CHECK_CUDA(cudaStreamSynchronize(cx.st));
       P.jobs_uploaded_for = cx.ws;
     }
-    PtrTable tbl;
-    memset(&tbl, 0, sizeof(tbl));
-    for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.params[i];
-    LAUNCHED(cx, CAT_PACK, launch_pack_all(tbl, reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off), (int)P.pack_jobs.size(), cx.ws,
-                                           P.split, cx.st));
+    if (!cx.skip_pack) {
+      PtrTable tbl;
+      memset(&tbl, 0, sizeof(tbl));
+      for (size_t i = 0; i < P.params.size(); ++i) tbl.p[i] = cx.params[i];
+      LAUNCHED(cx, CAT_PACK, launch_pack_all(tbl, reinterpret_cast<const PackJob*>(cx.ws + P.jobs_off), (int)P.pack_jobs.size(), cx.ws,
+                                             P.split, cx.st));
+    }
     TRef t = full(P, b_in);
     LAUNCHED(cx, CAT_RESAMPLE, launch_input_pack(cx.x, P.d.n_features, act_of(P, cx, t), nullptr, P.bufs[b_in].C, cx.st));
     return OK;
@@ -1187,6 +1190,10 @@ size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan) { return plan ? 
 
 int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
                           int save_for_backward, void* workspace, float* logits, void* stream) {
+  // save_for_backward: bit 0 = b200unet_plan_backward will follow; bit 1 = the parameters are unchanged since the previous
+  // forward on THIS workspace: keep its packed bf16 weights (tiled inference runs 9-27 forwards per volume on fixed weights)
+  const bool skip_pack = (save_for_backward & 2) != 0;
+  save_for_backward &= 1;
   if (save_for_backward && plan && plan->infer) {
     set_error("plan_forward: save_for_backward=1 on a plan created with inference_only=1");
     return E_INVALID;
@@ -1198,6 +1205,7 @@ int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* cons
   cx.params = params; cx.x = x; cx.logits = logits;
   cx.st = reinterpret_cast<cudaStream_t>(stream);
   cx.prof = plan->prof;
+  cx.skip_pack = skip_pack && plan->jobs_uploaded_for == cx.ws;   // only valid on a workspace that has been packed before
   plan->have_drop = dropout_scale != nullptr;
   if (dropout_scale) {
     float* dst = reinterpret_cast<float*>(cx.ws + plan->drop_off);

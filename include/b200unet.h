@@ -187,8 +187,10 @@ int b200unet_plan_num_params(const b200unet_plan* plan);
 int b200unet_plan_param_info(const b200unet_plan* plan, int i, int64_t shape[5], char* key, int key_cap);
 size_t b200unet_plan_workspace_bytes(const b200unet_plan* plan);
 /* forward: x NCDHW fp32 -> logits NCDHW fp32.  params: device array-of-pointers (host array of device pointers) to
- * the fp32 parameters.  dropout_scale: [N][C0] per-channel scale or NULL (eval).  save_for_backward != 0 states that
- * b200unet_plan_backward will follow (rejected on an inference_only plan, whose workspace keeps no activations). */
+ * the fp32 parameters.  dropout_scale: [N][C0] per-channel scale or NULL (eval).  save_for_backward: bit 0 states that
+ * b200unet_plan_backward will follow (rejected on an inference_only plan, whose workspace keeps no activations); bit 1
+ * states that the parameters are unchanged since the previous forward on this workspace (its packed bf16 weights are
+ * kept: tiled inference runs many forwards per volume on fixed weights). */
 int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* const* params, const float* dropout_scale,
                           int save_for_backward, void* workspace, float* logits, void* stream);
 /* backward: dlogits NCDHW fp32 -> grads[i] (fp32, same shapes as params; overwritten). */

@@ -248,6 +248,26 @@ def test_forward_only_plan_matches_training_plan_and_is_smaller(pkg):
         y_inf.sum().backward()
 
 
+def test_forward_only_plan_repacks_weights_after_an_update(pkg):
+    """forward-only plans keep their packed bf16 weights while no parameter changes (tiled inference); an in-place update
+    (optimizer step, load_state_dict) must be picked up by the next forward."""
+    kw = dict(n_features=2, n_outputs=2, base_width=8, encoder_blocks=[1, 1], decoder_blocks=[1, 1])
+    model = pkg.UNet3D(precision="split", **kw).to(DEV).eval()
+    x = torch.randn(1, 2, 16, 16, 16, device=DEV)
+    with torch.no_grad():
+        y0 = model(x)
+        y1 = model(x)                                      # packed weights reused
+        assert torch.equal(y0, y1)
+        for p in model.parameters():
+            p.mul_(1.5)                                    # bumps the version counters
+        y2 = model(x)
+        sd = {k: v / 1.5 for k, v in model.state_dict().items()}
+        model.load_state_dict(sd)
+        y3 = model(x)
+    assert float((y2 - y0).abs().max()) > 1e-3
+    assert float((y3 - y0).abs().max()) < 1e-4 * max(1.0, float(y0.abs().max()))
+
+
 def test_dice_accepts_soft_float_targets(pkg):
     g = torch.Generator().manual_seed(4)
     logits = torch.randn(2, 3, 9, 10, 11, generator=g)
