@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, p.cls_mode ? (8 * BN < 32 ? 32 : 8 * BN) : Cfg::TMEM_COLS);   // class mode: one accumulator per parity class
     tmem_relinquish();
   }
   if (warp >= 2) {
@@ -92,9 +92,14 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int cls = p.cls_mode ? (int)blockIdx.z : 0;   // parity class (pd, ph, pw) of the outputs this CTA produces
-  const int total_iters = p.cls_mode ? (int)p.cls_n[cls] * p.kchunks[0] * p.npass
-                                     : (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
+  // class mode: ONE CTA computes all eight parity classes of its voxel tile (27 tap products walked class by class into
+  // eight TMEM accumulators, then eight tile stores).  One CTA per class spent most of its life in set-up: 32768 CTAs of
+  // 1-8 K steps each took 0.47 ms for the 32-channel level-0 gradient.
+  int total_iters = (p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1]) * p.npass;
+  if (p.cls_mode) {
+    total_iters = 0;
+    for (int c = 0; c < 8; ++c) total_iters += (int)p.cls_n[c] * p.kchunks[0] * p.npass;
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent, one lane issues)
@@ -105,6 +110,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
         const int nt = p.ntaps[src];
         if (nt == 0) continue;
         const int ks = p.ksz[src], pad = p.pad[src], sd = p.stride[src];
+        for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
         const int ntap_loop = p.cls_mode ? (int)p.cls_n[cls] : nt;
         for (int ti = 0; ti < ntap_loop; ++ti) {
           int tap = ti, cw, ch, cd;
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
             }
           }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -138,17 +145,21 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
       constexpr uint32_t hi_d = desc_hi(Cfg::SBO, Cfg::LAYOUT);
       const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem0 = smem_u32(smem);
+      // class mode: iterations [cls_end[c-1], cls_end[c]) accumulate into accumulator c (TMEM columns c * BN ...)
+      int cur_cls = 0, cls_end = p.cls_mode ? (int)p.cls_n[0] * p.kchunks[0] * p.npass : total_iters, cls_first = 0;
       for (int it = 0; it < total_iters; ++it) {
+        while (it >= cls_end) { ++cur_cls; cls_first = it; cls_end += (int)p.cls_n[cur_cls] * p.kchunks[0] * p.npass; }
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES, 16);
         const uint32_t b_lo = desc_lo(smem0 + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, 16);
+        const uint32_t acc = tmem0 + cur_cls * BN;
         if (elect_one()) {   // one elected lane issues the stage (descriptors stay in uniform registers)
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)
-            umma_bf16(tmem0, desc_from(a_lo + 2 * k, hi_d), desc_from(b_lo + 2 * k, hi_d), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(acc, desc_from(a_lo + 2 * k, hi_d), desc_from(b_lo + 2 * k, hi_d), idesc, (it > cls_first || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
           if (it == total_iters - 1) umma_commit(tfull_bar);
         }
@@ -162,35 +173,42 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     const int wl = row % p.tw, hl = (row / p.tw) % p.th, dl = row / (p.tw * p.th);
     const int w = w0 + wl, h = h0 + hl, d = d0 + dl;
     const bool valid = (w < p.Wo) && (h < p.Ho) && (d < p.Do);
-    // side inputs (residual) are indexed in the OUTPUT tensor: in class mode that is voxel 2j + p of a 2x grid
-    const long long vox = p.cls_mode
-        ? (((long long)n * (2 * p.Do) + 2 * d + ((cls >> 2) & 1)) * (2 * p.Ho) + 2 * h + ((cls >> 1) & 1)) * (2 * p.Wo) + 2 * w + (cls & 1)
-        : (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-    conv_epilogue_prefetch(p, n0, BN, vox, valid);
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
     const bool want_stats = (p.mode == 0) ? (p.stats != nullptr) : (p.bstats != nullptr);
     const bool edge = p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d == p.Do - 1);
-    // all MMAs have completed (tfull) => every pipeline stage has been consumed: the stage memory is free and is reused
-    // as the output staging tile [BN/CBO boxes][128 rows][CBO] (+ lo tile), TMA-stored below
     const bool split = p.out_lo != nullptr;
-    conv_epilogue_tile<BN>(p, tmem_base, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, row, split);
-    fence_proxy_async();
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      constexpr int CBO = BN < 64 ? BN : 64;
-      const CUtensorMap* mo_hi = p.cls_mode ? &cmaps.oc[cls][0] : &maps.o[0];
-      const CUtensorMap* mo_lo = p.cls_mode ? &cmaps.oc[cls][1] : &maps.o[1];
-#pragma unroll
-      for (int cb = 0; cb < BN / CBO; ++cb) {
-        if (n0 + cb * CBO < p.Cout) {
-          tma_store_5d(mo_hi, smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
-          if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
-        }
+    constexpr int CBO = BN < 64 ? BN : 64;
+    for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
+      // side inputs (residual) are indexed in the OUTPUT tensor: in class mode that is voxel 2j + p of a 2x grid
+      const long long vox = p.cls_mode
+          ? (((long long)n * (2 * p.Do) + 2 * d + ((cls >> 2) & 1)) * (2 * p.Ho) + 2 * h + ((cls >> 1) & 1)) * (2 * p.Wo) + 2 * w + (cls & 1)
+          : (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+      conv_epilogue_prefetch(p, n0, BN, vox, valid);
+      if (cls == 0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+      } else {
+        if (threadIdx.x == 64) tma_store_wait_read0();    // the previous class's stores have read the staging tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      tma_store_commit();
+      // all MMAs have completed (tfull) => every pipeline stage has been consumed: the stage memory is free and is reused
+      // as the output staging tile [BN/CBO boxes][128 rows][CBO] (+ lo tile), TMA-stored below
+      conv_epilogue_tile<BN>(p, tmem_base + cls * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, row, split);
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const CUtensorMap* mo_hi = p.cls_mode ? &cmaps.oc[cls][0] : &maps.o[0];
+        const CUtensorMap* mo_lo = p.cls_mode ? &cmaps.oc[cls][1] : &maps.o[1];
+#pragma unroll
+        for (int cb = 0; cb < BN / CBO; ++cb) {
+          if (n0 + cb * CBO < p.Cout) {
+            tma_store_5d(mo_hi, smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+            if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+          }
+        }
+        tma_store_commit();
+      }
     }
     if (want_stats) {
       const int e = threadIdx.x - 64;
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     if (threadIdx.x == 64) tma_store_wait_all();   // the staging tile must outlive the bulk store
   }
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, p.cls_mode ? (8 * BN < 32 ? 32 : 8 * BN) : Cfg::TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -291,7 +309,8 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
       B200_REQUIRE(op.src[s].x.lo && op.src[s].w_lo, E_INVALID, "igemm_conv: split mode needs lo parts on every source");
   }
   const int KC = cin_max > 32 ? 64 : cin_max > 16 ? 32 : 16;
-  const int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
+  int BN = out.C > 64 ? 128 : out.C > 32 ? 64 : out.C > 16 ? 32 : 16;
+  if (op.cls_mode && BN > 64) BN = 64;   // eight accumulators of BN columns share the 512 TMEM columns
   const Swz swz = swz_for_bytes(KC * 2);
   for (int s = 0; s < op.nsrc; ++s) {
     const ConvSrc& c = op.src[s];
@@ -362,7 +381,7 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     a.coef = reinterpret_cast<const float4*>(op.coef); a.coef_ld = op.coef_ld;
     a.slope = op.slope; a.bstats = op.bstats;
   }
-  dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN), op.cls_mode ? 8u : 1u);
+  dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN), 1u);
 #define B200_CONV_CASE(bn, kc) \
   if (BN == bn && KC == kc) return launch_cfg<bn, kc>(maps, a, grid, st, cmaps);
   B200_CONV_CASE(16, 16) B200_CONV_CASE(16, 32) B200_CONV_CASE(16, 64)
