@@ -1213,7 +1213,20 @@ int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* cons
                         cx.st) != cudaSuccess) { set_error("plan_forward: dropout copy failed"); return E_CUDA; }
     cx.drop = dst;
   }
-  for (auto& op : plan->fwd) { int s = op(cx); if (s != OK) return s; }
+  static const bool capdbg = getenv("B200UNET_CAPTURE_DEBUG") != nullptr;
+  for (auto& op : plan->fwd) {
+    int s = op(cx);
+    if (s != OK) return s;
+    if (capdbg) {   // which op (if any) invalidates an ongoing CUDA-graph capture of this stream?
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaError_t e = cudaStreamIsCapturing(cx.st, &cs);
+      if (e != cudaSuccess || cs == cudaStreamCaptureStatusInvalidated) {
+        set_error("plan_forward: stream capture invalidated at op '%s' (%s)", cx.label ? cx.label : "?", cudaGetErrorString(e));
+        cudaGetLastError();
+        return E_CUDA;
+      }
+    }
+  }
   plan->last_launches = cx.launches;
   return OK;
 }
@@ -1229,7 +1242,20 @@ int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const floa
   cx.st = reinterpret_cast<cudaStream_t>(stream);
   cx.prof = plan->prof;
   if (plan->have_drop) cx.drop = reinterpret_cast<float*>(cx.ws + plan->drop_off);
-  for (auto& op : plan->bwd) { int s = op(cx); if (s != OK) return s; }
+  static const bool capdbg = getenv("B200UNET_CAPTURE_DEBUG") != nullptr;
+  for (auto& op : plan->bwd) {
+    int s = op(cx);
+    if (s != OK) return s;
+    if (capdbg) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaError_t e = cudaStreamIsCapturing(cx.st, &cs);
+      if (e != cudaSuccess || cs == cudaStreamCaptureStatusInvalidated) {
+        set_error("plan_backward: stream capture invalidated at op '%s' (%s)", cx.label ? cx.label : "?", cudaGetErrorString(e));
+        cudaGetLastError();
+        return E_CUDA;
+      }
+    }
+  }
   plan->last_launches = cx.launches;
   return OK;
 }
