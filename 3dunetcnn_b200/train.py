@@ -67,7 +67,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, criterion, optimizer, images_shape, target_shape, target_dtype=torch.uint8, device=None,
-                 grad_sync=None, warmup: int = 2, capture_error_mode: str = "thread_local"):
+                 grad_sync=None, warmup: int = 2, capture_error_mode: str = "global"):
         self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
         device = device or next(model.parameters()).device
         self.images = torch.zeros(tuple(images_shape), dtype=torch.float32, device=device)
@@ -76,8 +76,9 @@ class GraphedTrainStep:
         self.loss = None
         self.warmup = int(warmup)
         self.device = device
-        # "thread_local": CUDA calls of OTHER threads (a DataLoader's pin-memory thread, NCCL's watchdog) do not invalidate
-        # the capture; everything this thread issues inside the capture is stream-ordered work on the capture stream
+        # "global" (torch's default).  Measured on B200 / torch 2.11 (tools/graph_debug.py): "global" and "relaxed" capture the
+        # step, "thread_local" does not -- autograd runs the backward of the step on its device worker thread, which may not
+        # enqueue into a stream another thread is capturing in thread-local mode
         self.capture_error_mode = capture_error_mode
 
     def _capture(self):
