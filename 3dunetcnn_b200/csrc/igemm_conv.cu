@@ -177,12 +177,15 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     const bool edge = p.zero_last && (w == p.Wo - 1 || h == p.Ho - 1 || d == p.Do - 1);
     const bool split = p.out_lo != nullptr;
     constexpr int CBO = BN < 64 ? BN : 64;
-    for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
-      // side inputs (residual) are indexed in the OUTPUT tensor: in class mode that is voxel 2j + p of a 2x grid
-      const long long vox = p.cls_mode
+    // side inputs (residual) are indexed in the OUTPUT tensor: in class mode that is voxel 2j + p of a 2x grid
+    auto vox_of = [&](int cls) -> long long {
+      return p.cls_mode
           ? (((long long)n * (2 * p.Do) + 2 * d + ((cls >> 2) & 1)) * (2 * p.Ho) + 2 * h + ((cls >> 1) & 1)) * (2 * p.Wo) + 2 * w + (cls & 1)
           : (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-      conv_epilogue_prefetch(p, n0, BN, vox, valid);
+    };
+    for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) conv_epilogue_prefetch(p, n0, BN, vox_of(cls), valid);   // -> L2 while the MMAs run
+    for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
+      const long long vox = vox_of(cls);
       if (cls == 0) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
         mbar_wait(tfull_bar, 0);

@@ -147,14 +147,14 @@ __global__ void __launch_bounds__(256) k_unpack_all_tiled(PtrTable grads, const 
 
 int launch_pack_all_tiled(const PtrTable& params, const PackJob* jobs_dev, int njobs, uint8_t* ws, bool split, cudaStream_t st) {
   if (njobs == 0) return OK;
-  k_pack_all_tiled<<<dim3(64, njobs), 256, 0, st>>>(params, jobs_dev, ws, split ? 1 : 0);
+  k_pack_all_tiled<<<dim3(256, njobs), 256, 0, st>>>(params, jobs_dev, ws, split ? 1 : 0);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
 
 int launch_unpack_all_tiled(const PtrTable& grads, const PackJob* jobs_dev, int njobs, const uint8_t* ws, cudaStream_t st) {
   if (njobs == 0) return OK;
-  k_unpack_all_tiled<<<dim3(64, njobs), 256, 0, st>>>(grads, jobs_dev, ws);
+  k_unpack_all_tiled<<<dim3(256, njobs), 256, 0, st>>>(grads, jobs_dev, ws);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
@@ -280,7 +280,7 @@ int launch_upsample2x_bwd_tiled(const Act& dy, const Act& dx, cudaStream_t st) {
 // (Ci x 8) fp32 tile of dW in registers over its whole grid-stride loop; reduced by warp shuffles over the lanes that share
 // the chunk, shared-memory atomics across warps, then one global atomic per element per block.
 template <int CI8>
-__global__ void __launch_bounds__(256) k_wgrad_1x1_narrow(Act a, Act dy, float* __restrict__ dw, int Cop) {
+__global__ void __launch_bounds__(256, CI8 == 1 ? 2 : 1) k_wgrad_1x1_narrow(Act a, Act dy, float* __restrict__ dw, int Cop) {
   extern __shared__ float s_dw[];   // [Ci][Co]
   const int Ci = CI8 * 8, Co = dy.C;
   for (int i = threadIdx.x; i < Ci * Co; i += blockDim.x) s_dw[i] = 0.f;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) k_wgrad_1x1_narrow(Act a, Act dy, float* 
   const long long stride = (long long)gridDim.x * vper;
   // UF voxels in flight per thread: all loads of an iteration are issued before the first FMA (one voxel per iteration left
   // the kernel latency-bound at ~1.3 TB/s)
-  constexpr int UF = 4;
+  constexpr int UF = 2;
   for (long long v0 = (long long)blockIdx.x * vper + vslot; v0 < total; v0 += UF * stride) {
     uint4 gq[UF], xq[UF][CI8];
 #pragma unroll
@@ -373,7 +373,7 @@ int launch_wgrad_1x1_narrow(const WgradOp& op, cudaStream_t st) {
   const int c8n = op.dy.C / 8;
   const int vper = 256 / c8n;
   const long long want = (op.a.voxels() + vper - 1) / vper;
-  const int blocks = (int)(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4);
+  const int blocks = (int)(want < 148 * 6 ? (want > 0 ? want : 1) : 148 * 6);
   const size_t smem = (size_t)op.a.C * op.dy.C * sizeof(float);
   if (op.a.C == 8) k_wgrad_1x1_narrow<1><<<blocks, 256, smem, st>>>(op.a, op.dy, op.dw, op.Cop);
   else k_wgrad_1x1_narrow<2><<<blocks, 256, smem, st>>>(op.a, op.dy, op.dw, op.Cop);
