@@ -168,6 +168,8 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   h.hsplit = hsplit;
   h.split = split ? 1 : 0;
   h.dense1 = dense1 ? 1 : 0;
+  static const bool prefetch = getenv("B200UNET_HALO_PREFETCH") && atoi(getenv("B200UNET_HALO_PREFETCH")) == 1;
+  h.prefetch = prefetch ? 1 : 0;
   h.dbg = nullptr;
   if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);

@@ -56,6 +56,8 @@ struct HaloArgs {
   int nout;          // output staging buffers (2 or 4), each OUT_TILE * (split ? 2 : 1) bytes
   int split;
   int dense1;        // 1x1x1 sources are loaded as one dense (KC, 8, 16, TD) box instead of a halo neighbourhood
+  int prefetch;      // L2-prefetch the later planes' side-input rows at tile start (measured: the prefetch instructions themselves
+                     // stall the issuing warp ~450 cycles each; B200UNET_HALO_PREFETCH=1 re-enables them)
   long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
 #define EPI_STAMP(idx) \
@@ -447,8 +449,9 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       EPI_STAMP(41);
       load_side(vox0 + dpl0 * plane, n0, 0, valid_wh && (d0 + dpl0 < p.Do) && dpl0 < TD);   // lands while the MMAs still run
       EPI_STAMP(42);
-      for (int dpl = dpl0 + pstep; dpl < TD; dpl += pstep)     // the later planes' rows -> L2
-        conv_epilogue_prefetch(p, n0 + jb * 16, NJ * 16, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
+      if (hp.prefetch)
+        for (int dpl = dpl0 + pstep; dpl < TD; dpl += pstep)     // the later planes' rows -> L2
+          conv_epilogue_prefetch(p, n0 + jb * 16, NJ * 16, vox0 + dpl * plane, valid_wh && (d0 + dpl < p.Do));
       EPI_STAMP(43);
       const uint32_t as = ti % Cfg::NACC;
       if (warp == 2) HALO_STAMP(2, 0);
