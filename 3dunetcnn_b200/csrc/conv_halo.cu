@@ -167,6 +167,8 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   h.ntiles = ntiles;
   h.hsplit = hsplit;
   h.split = split ? 1 : 0;
+  h.fd_nt = make_fastdiv((unsigned)ntiles); h.fd_w = make_fastdiv((unsigned)a.tiles_w);
+  h.fd_h = make_fastdiv((unsigned)a.tiles_h); h.fd_d = make_fastdiv((unsigned)a.tiles_d);
   h.dense1 = dense1 ? 1 : 0;
   static const bool prefetch = getenv("B200UNET_HALO_PREFETCH") && atoi(getenv("B200UNET_HALO_PREFETCH")) == 1;
   h.prefetch = prefetch ? 1 : 0;

@@ -48,6 +48,27 @@ struct HaloCfg {
   static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
 };
 
+// division by a run-time constant as multiply-high + shift (q = umulhi(x, mul) >> shr for x < 2^31; CUTLASS FastDivmod scheme):
+// the five div/mod pairs of the tile decode cost ~700 cycles per tile in the epilogue warps (tools/halo_timeline.py)
+struct FastDiv {
+  unsigned mul, shr, div;
+};
+static inline FastDiv make_fastdiv(unsigned d) {
+  FastDiv f;
+  f.div = d;
+  if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+  unsigned l = 31u - (unsigned)__builtin_clz(d);
+  if (d & (d - 1)) ++l;                       // ceil(log2(d))
+  const unsigned p = 31u + l;
+  f.mul = (unsigned)((((unsigned long long)1 << p) + d - 1) / d);
+  f.shr = p - 32u;
+  return f;
+}
+__device__ __forceinline__ void fast_divmod(int x, const FastDiv& f, int& q, int& r) {
+  q = f.div > 1 ? (int)(__umulhi((unsigned)x, f.mul) >> f.shr) : x;
+  r = x - q * (int)f.div;
+}
+
 struct HaloArgs {
   int tiles_total;   // N * tiles_d * tiles_h * tiles_w * ntiles
   int ntiles;        // output-channel tiles
@@ -55,6 +76,7 @@ struct HaloArgs {
   int nb;            // weight ring depth (stages of TPB taps)
   int nout;          // output staging buffers (2 or 4), each OUT_TILE * (split ? 2 : 1) bytes
   int split;
+  FastDiv fd_nt, fd_w, fd_h, fd_d;   // ntiles, tiles_w, tiles_h, tiles_d
   int dense1;        // 1x1x1 sources are loaded as one dense (KC, 8, 16, TD) box instead of a halo neighbourhood
   int prefetch;      // L2-prefetch the later planes' side-input rows at tile start (measured: the prefetch instructions themselves
                      // stall the issuing warp ~450 cycles each; B200UNET_HALO_PREFETCH=1 re-enables them)
@@ -130,11 +152,11 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     uint32_t hi = 0, bi = 0, ti = 0;
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       int t = tile;
-      const int nt = t % hp.ntiles; t /= hp.ntiles;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h; t /= p.tiles_h;
-      const int dt = t % p.tiles_d;
-      const int n = t / p.tiles_d;
+      int nt, wt, ht, dt, n;
+      fast_divmod(t, hp.fd_nt, t, nt);
+      fast_divmod(t, hp.fd_w, t, wt);
+      fast_divmod(t, hp.fd_h, t, ht);
+      fast_divmod(t, hp.fd_d, n, dt);
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
       if (halo_role) HALO_STAMP(0, 0);
       for (int g = 0; g < groups0 + groups1; ++g) {
@@ -419,11 +441,11 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       EPI_STAMP(40);
       int t = tile;
-      const int nt = t % hp.ntiles; t /= hp.ntiles;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h; t /= p.tiles_h;
-      const int dt = t % p.tiles_d;
-      const int n = t / p.tiles_d;
+      int nt, wt, ht, dt, n;
+      fast_divmod(t, hp.fd_nt, t, nt);
+      fast_divmod(t, hp.fd_w, t, wt);
+      fast_divmod(t, hp.fd_h, t, ht);
+      fast_divmod(t, hp.fd_d, n, dt);
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
       if (n != cur_n || n0 != cur_n0) {
         if (RUN && want_stats && cur_n >= 0) {

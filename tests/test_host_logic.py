@@ -247,3 +247,23 @@ def test_transposed_conv_k2s2_roles():
     assert torch.allclose(dx, x.grad)
     dw = torch.stack([torch.einsum("cj,oj->co", x[0].detach(), du[0, :, t::2]) for t in (0, 1)], dim=-1)
     assert torch.allclose(dw, w.grad)
+
+
+def test_tile_decode_fast_division_restatement():
+    """conv_halo_kernel.cuh make_fastdiv / fast_divmod: q = umulhi(x, mul) >> shr with p = 31 + ceil(log2 d), mul = ceil(2^p / d),
+    shr = p - 32 must equal x // d for every tile index (x < 2^31) and every tile-count divisor."""
+    import random
+
+    def mk(d):
+        if d <= 1:
+            return 0, 0
+        lg = d.bit_length() - 1 + (1 if d & (d - 1) else 0)
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+    rnd = random.Random(0)
+    for d in list(range(1, 300)) + [511, 512, 513, 1000, 4096, 65535]:
+        mul, shr = mk(d)
+        assert mul < 2 ** 32
+        for x in list(range(0, 600)) + [rnd.randrange(0, 2 ** 31) for _ in range(300)] + [2 ** 31 - 1]:
+            q = (((x * mul) >> 32) >> shr) if d > 1 else x
+            assert q == x // d and x - q * d == x % d
