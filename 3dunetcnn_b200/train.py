@@ -92,13 +92,27 @@ class GraphedTrainStep:
                 self.optimizer.zero_grad(set_to_none=True)
                 loss = self.criterion(model(self.images), self.target)
                 loss.backward()
+                # No autograd graph of the warm-up may outlive this line.  While one is alive it keeps the parameters'
+                # AccumulateGrad nodes alive, and those remember the stream they were created on (this side stream); the
+                # captured backward would reuse them, autograd would synchronise the capturing stream with that
+                # non-capturing one, and the capture ends as cudaErrorStreamCaptureInvalidated (measured on B200 /
+                # torch 2.11 with tools/graph_debug2.py: 'replica' fails, 'del_loss' captures).
+                del loss
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         model._overwrite_grads = True
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
-            self.loss = self.criterion(model(self.images), self.target)
-            self.loss.backward()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
+                self.loss = self.criterion(model(self.images), self.target)
+                self.loss.backward()
+        except Exception as e:
+            self.graph = None
+            self.loss = None
+            raise RuntimeError(
+                "GraphedTrainStep: CUDA-graph capture of the training step failed (%s).  A loss (or any tensor with a grad_fn) of "
+                "an earlier eager step of this model that is still referenced makes autograd synchronise the capturing stream "
+                "with the stream of that step: drop those references before the first graphed step." % (e,)) from e
 
     def step(self, images, target):
         if self.graph is None:
