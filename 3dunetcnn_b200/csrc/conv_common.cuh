@@ -11,6 +11,8 @@ struct ConvMaps {
   CUtensorMap a[2][2];  // [source][hi/lo]
   CUtensorMap b[2][2];
   CUtensorMap o[2];     // output tile stores (hi/lo): the epilogue stages 128 x BN tiles in shared memory and TMA-stores them
+  CUtensorMap side;     // halo kernel: the epilogue's side input (residual / GroupNorm input), box = one output plane tile; only
+                        // used to request its tiles into L2 ahead of the epilogue (cp.async.bulk.prefetch.tensor)
 };
 // parity-class mode of the streaming kernel (stride-2 data gradient): one output map per class and hi/lo
 struct ConvClassMaps {

@@ -172,6 +172,16 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   h.dense1 = dense1 ? 1 : 0;
   static const bool prefetch = getenv("B200UNET_HALO_PREFETCH") && atoi(getenv("B200UNET_HALO_PREFETCH")) == 1;
   h.prefetch = prefetch ? 1 : 0;
+  // side input of the epilogue: one (BN, 8, 16, 1) box per output plane tile, only ever prefetched into L2
+  static const bool no_side_pf = getenv("B200UNET_HALO_SIDE_PF") && atoi(getenv("B200UNET_HALO_SIDE_PF")) == 0;   // A/B switch
+  const Act* side = op.mode == 1 ? op.gn_x : op.res;
+  if (side && side->hi && !no_side_pf) {
+    const int bc = BN < side->C ? BN : side->C;
+    B200_TRY(make_act_map(&maps.side, side->hi, side->N, side->D, side->H, side->W, side->C, side->ld, bc, 8, 16, 1, 1, SWZ_NONE));
+    h.side_pf = 1;
+  } else {
+    maps.side = maps.o[0];
+  }
   h.dbg = nullptr;
   if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);

@@ -80,6 +80,7 @@ struct HaloArgs {
   int dense1;        // 1x1x1 sources are loaded as one dense (KC, 8, 16, TD) box instead of a halo neighbourhood
   int prefetch;      // L2-prefetch the later planes' side-input rows at tile start (measured: the prefetch instructions themselves
                      // stall the issuing warp ~450 cycles each; B200UNET_HALO_PREFETCH=1 re-enables them)
+  int side_pf;       // the halo producer requests each tile's side-input planes into L2 (maps.side) ahead of the epilogue
   long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
 #define EPI_STAMP(idx) \
@@ -159,6 +160,14 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       fast_divmod(t, hp.fd_d, n, dt);
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
       if (halo_role) HALO_STAMP(0, 0);
+      if (halo_role && hp.side_pf) {
+        // the epilogue reads one row of the side input (residual / GroupNorm input) per thread and plane straight from global
+        // memory, one plane ahead at most (registers): from HBM that latency bounded the drain (~4.1 K cycles per plane of
+        // 128 x 64 in the GroupNorm-backward epilogue, profiles/r02_halo_timeline.txt).  This warp runs 1-3 tiles ahead of
+        // the epilogue: it asks the TMA unit to pull the tile's side planes into L2 now, so those loads become L2 hits.
+        for (int dpl = 0; dpl < TD; ++dpl)
+          if (d0 + dpl < p.Do) tma_prefetch_l2_5d_if(issue, &maps.side, n0, w0, h0, d0 + dpl, n);
+      }
       for (int g = 0; g < groups0 + groups1; ++g) {
         const int src = g < groups0 ? 0 : 1;
         const int kc = src == 0 ? g : g - groups0;

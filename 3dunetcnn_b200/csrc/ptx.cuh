@@ -116,6 +116,14 @@ __device__ __forceinline__ void tma_load_5d_if(uint32_t issue, void* smem_dst, c
       "r"(c3), "r"(c4), "r"(issue)
       : "memory");
 }
+// Side-effect-free request to pull one box of a tiled map into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_5d_if(uint32_t issue, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];\n\t}\n"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(issue)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_if(uint32_t issue, void* smem_dst, const CUtensorMap* map, uint64_t* bar,
                                                int c0, int c1, int c2) {
   asm volatile(
