@@ -8,6 +8,8 @@ to the same bars.
 Tolerances (north_star): logits rel-L2 <= 1e-3 and |dDice| <= 1e-3 in `split` precision; every gradient norm within
 3 % and cosine > 0.999.  In single-pass `bf16` the Dice bound holds and the logits carry bf16 operand rounding
 (<= 4e-2); its gradients are bounded against torch's own bf16 autocast in test_gpu_bf16_vs_autocast.py."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -65,6 +67,14 @@ def _ours(pkg, o, precision):
     return res
 
 
+def _record(line):
+    # measured values of the bounds below, kept next to the other GPU artefacts when the scratch directory exists
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "northstar_measured.txt"), "a") as f:
+            f.write(line + "\n")
+
+
 def _rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
@@ -94,7 +104,11 @@ def _check_bf16(pkg, o):
         den += float((r ** 2).sum())
         if np.linalg.norm(r) > 0:
             assert abs(np.linalg.norm(g) / np.linalg.norm(r) - 1.0) < 0.25, (k, np.linalg.norm(g), np.linalg.norm(r))
-    assert (num / den) ** 0.5 < 0.35                             # whole gradient vector (per tensor: see the autocast test)
+    whole = (num / den) ** 0.5
+    worst = max(abs(np.linalg.norm(g) / np.linalg.norm(o["grads"][k]) - 1.0) for k, g in grads.items() if np.linalg.norm(o["grads"][k]) > 0)
+    _record("bf16 mode vs fp64 oracle: logits rel-L2 %.3e, dice diff %.3e, whole-gradient rel-L2 %.3e, worst norm deviation %.3e"
+            % (_rel(logits, o["logits"]), abs(dice - o["dice"]), whole, worst))
+    assert whole < 0.35                                          # whole gradient vector (per tensor: see the autocast test)
 
 
 def test_c2_size_split_precision_matches_cpu_oracle(pkg, oracle_c2):
