@@ -7,7 +7,9 @@ to the same bars.
 
 Tolerances (north_star): logits rel-L2 <= 1e-3 and |dDice| <= 1e-3 in `split` precision; every gradient norm within
 3 % and cosine > 0.999.  In single-pass `bf16` the Dice bound holds and the logits carry bf16 operand rounding
-(<= 4e-2); its gradients are bounded against torch's own bf16 autocast in test_gpu_bf16_vs_autocast.py."""
+(<= 2e-2, measured 4.9e-3), the whole gradient vector is within 3e-2 rel-L2 of the fp64-pinned oracle's (measured
+5.6e-3 / 6.7e-3) and every gradient norm within 5 % (measured <= 5.7e-3); per-tensor bounds against torch's own bf16
+autocast are in test_gpu_bf16_vs_autocast.py."""
 import os
 
 import numpy as np
@@ -95,7 +97,7 @@ def _check_split(pkg, o):
 def _check_bf16(pkg, o):
     logits, dice, grads = _ours(pkg, o, "bf16")
     assert abs(dice - o["dice"]) < 1e-3 * abs(o["dice"])
-    assert _rel(logits, o["logits"]) < 4e-2
+    assert _rel(logits, o["logits"]) < 2e-2                      # measured 4.9e-3 (bf16 operand rounding through 40 layers)
     num = den = 0.0
     for k, g in grads.items():
         r = o["grads"][k]
@@ -103,12 +105,12 @@ def _check_bf16(pkg, o):
         num += float(((g - r) ** 2).sum())
         den += float((r ** 2).sum())
         if np.linalg.norm(r) > 0:
-            assert abs(np.linalg.norm(g) / np.linalg.norm(r) - 1.0) < 0.25, (k, np.linalg.norm(g), np.linalg.norm(r))
+            assert abs(np.linalg.norm(g) / np.linalg.norm(r) - 1.0) < 5e-2, (k, np.linalg.norm(g), np.linalg.norm(r))
     whole = (num / den) ** 0.5
     worst = max(abs(np.linalg.norm(g) / np.linalg.norm(o["grads"][k]) - 1.0) for k, g in grads.items() if np.linalg.norm(o["grads"][k]) > 0)
     _record("bf16 mode vs fp64 oracle: logits rel-L2 %.3e, dice diff %.3e, whole-gradient rel-L2 %.3e, worst norm deviation %.3e"
             % (_rel(logits, o["logits"]), abs(dice - o["dice"]), whole, worst))
-    assert whole < 0.35                                          # whole gradient vector (per tensor: see the autocast test)
+    assert whole < 3e-2              # measured 5.6e-3 (C2) / 6.7e-3 (C3 crop); worst norm deviation measured 3.1e-3 / 5.7e-3
 
 
 def test_c2_size_split_precision_matches_cpu_oracle(pkg, oracle_c2):
