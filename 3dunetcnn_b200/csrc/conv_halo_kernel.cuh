@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
                                                                       const HaloArgs hp) {
   using Cfg = HaloCfg<KC, BN, TD, NI, KW>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space and every
+  // shared-memory access below would compile to a generic LD.E / ST.E (ncu source view, round 2) instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int out_buf_bytes = Cfg::OUT_TILE * (hp.split ? 2 : 1);
   uint8_t* smem_halo = smem;
   uint8_t* smem_out = smem + Cfg::NHALO * Cfg::HALO_BYTES;

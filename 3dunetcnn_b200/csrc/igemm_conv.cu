@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
                                                     const __grid_constant__ ConvClassMaps cmaps) {
   using Cfg = ConvCfg<BN, KC>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space and every
+  // shared-memory access below would compile to a generic LD.E / ST.E (ncu source view, round 2) instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + Cfg::PIPE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;

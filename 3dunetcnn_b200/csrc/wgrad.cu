@@ -65,7 +65,9 @@ template <int CB, int BN>
 __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
   using Cfg = WgradCfg<CB, BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space and every
+  // shared-memory access below would compile to a generic LD.E / ST.E (ncu source view, round 2) instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_d = smem + WG_A_STAGES * WG_A_BYTES;
   uint8_t* aux = smem_d + WG_D_STAGES * Cfg::D_STAGE;

@@ -1,6 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-TAG=${1:-r02i}
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_conv_halo -s 2 -c 1 -f -o gpurun_out/${TAG}_halo_mode1_32_64_128 python tools/halo_timeline.py 32 64 128 mode1 > gpurun_out/ncu_m1.log 2>&1; tail -2 gpurun_out/ncu_m1.log
-ls -la gpurun_out/*.ncu-rep
+TAG=${1:-r02j}
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -q -x 2>&1 | tail -3
+timeout 600 python tools/layer_times.py gpurun_out/${TAG}_layer_times.csv > gpurun_out/${TAG}_layer_times.log 2>&1; head -1 gpurun_out/${TAG}_layer_times.log; tail -1 gpurun_out/${TAG}_layer_times.log
+for a in "32 32 128 res" "32 64 128 mode1"; do
+  echo "## $a" >> gpurun_out/${TAG}_halo_timeline.txt
+  timeout 120 python tools/halo_timeline.py $a >> gpurun_out/${TAG}_halo_timeline.txt 2>&1
+done
+grep "steady-state\|epilogue warp 2" gpurun_out/${TAG}_halo_timeline.txt
