@@ -172,16 +172,14 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   h.dense1 = dense1 ? 1 : 0;
   static const bool prefetch = getenv("B200UNET_HALO_PREFETCH") && atoi(getenv("B200UNET_HALO_PREFETCH")) == 1;
   h.prefetch = prefetch ? 1 : 0;
-  // side input of the epilogue: one (BN, 8, 16, 1) box per output plane tile, only ever prefetched into L2
-  static const bool no_side_pf = getenv("B200UNET_HALO_SIDE_PF") && atoi(getenv("B200UNET_HALO_SIDE_PF")) == 0;   // A/B switch
+  // side input of the epilogue (residual / GroupNorm input): same box and swizzle as the output tile stores, so that the lean
+  // epilogues can TMA-load it straight into the output staging buffers (HaloArgs::side_ring)
+  static const bool no_ring = getenv("B200UNET_HALO_SIDE_RING") && atoi(getenv("B200UNET_HALO_SIDE_RING")) == 0;   // A/B switch
   const Act* side = op.mode == 1 ? op.gn_x : op.res;
-  if (side && side->hi && !no_side_pf) {
-    const int bc = BN < side->C ? BN : side->C;
-    B200_TRY(make_act_map(&maps.side, side->hi, side->N, side->D, side->H, side->W, side->C, side->ld, bc, 8, 16, 1, 1, SWZ_NONE));
-    h.side_pf = 1;
-  } else {
-    maps.side = maps.o[0];
-  }
+  maps.side = maps.o[0];
+  if (side && side->hi)
+    B200_TRY(make_act_map(&maps.side, side->hi, side->N, side->D, side->H, side->W, side->C, side->ld, cbo, 8, 16, 1, 1,
+                          swz_for_bytes(cbo * 2)));
   h.dbg = nullptr;
   if (const char* e = getenv("B200UNET_HALO_DBG")) h.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   h.tiles_total = (int)tiles_for(TD);
@@ -203,9 +201,15 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   if (kws == 3 && !halo_fits(KC, BN, TD, split, 3)) kws = 1;
   // epilogue variant: the lean bodies when none of the rare options is in play
   static const bool no_lean = getenv("B200UNET_HALO_GENERIC_EPILOGUE") != nullptr;   // A/B switch
-  const bool lean = !no_lean && !split && !op.scale && !op.bias && !op.zero_last;
-  if (lean && op.mode == 0) return launch_halo_ev1(KC, BN, TD, kws, maps, a, h, grid, st);
-  if (lean && op.mode == 1) return launch_halo_ev2(KC, BN, TD, kws, maps, a, h, grid, st);
+  const bool lean = !no_lean && !split && !op.scale && !op.bias && !op.zero_last && !(no_ring && side && side->hi);
+  if (lean) {
+    h.side_ring = (side && side->hi) ? 1 : 0;
+    int rc = op.mode == 0 ? launch_halo_ev1(KC, BN, TD, kws, maps, a, h, grid, st) : launch_halo_ev2(KC, BN, TD, kws, maps, a, h, grid, st);
+    if (rc == HALO_NO_RING && kws == 3)   // three-box weight stages leave no room: one box per stage with the ring
+      rc = op.mode == 0 ? launch_halo_ev1(KC, BN, TD, 1, maps, a, h, grid, st) : launch_halo_ev2(KC, BN, TD, 1, maps, a, h, grid, st);
+    if (rc != HALO_NO_RING) return rc;
+    h.side_ring = 0;     // three staging buffers per group do not fit: generic variant, side rows through registers
+  }
   return launch_halo_table<0>(KC, BN, TD, kws, maps, a, h, grid, st);
 }
 

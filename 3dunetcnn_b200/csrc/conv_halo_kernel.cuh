@@ -45,7 +45,7 @@ struct HaloCfg {
   static constexpr bool COLSPLIT = BN >= 64;                // epilogue groups split the columns (else the planes)
   static constexpr bool RUN = BN <= 64;                     // register-resident running statistics (<= 32 columns per thread)
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
-  static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 1024, "barrier area overflow");
+  static_assert((2 * NHALO + 2 * NB_MAX + 2 * NACC) * 8 + 8 <= 768, "barrier area overflow");   // side_full[6] sits at +768
 };
 
 // division by a run-time constant as multiply-high + shift (q = umulhi(x, mul) >> shr for x < 2^31; CUTLASS FastDivmod scheme):
@@ -69,6 +69,8 @@ __device__ __forceinline__ void fast_divmod(int x, const FastDiv& f, int& q, int
   r = x - q * (int)f.div;
 }
 
+static constexpr int HALO_NO_RING = -1000;   // internal: the side-ring staging buffers do not fit this configuration
+
 struct HaloArgs {
   int tiles_total;   // N * tiles_d * tiles_h * tiles_w * ntiles
   int ntiles;        // output-channel tiles
@@ -80,7 +82,8 @@ struct HaloArgs {
   int dense1;        // 1x1x1 sources are loaded as one dense (KC, 8, 16, TD) box instead of a halo neighbourhood
   int prefetch;      // L2-prefetch the later planes' side-input rows at tile start (measured: the prefetch instructions themselves
                      // stall the issuing warp ~450 cycles each; B200UNET_HALO_PREFETCH=1 re-enables them)
-  int side_pf;       // the halo producer requests each tile's side-input planes into L2 (maps.side) ahead of the epilogue
+  int side_ring;     // lean epilogues: the side input (residual / GroupNorm input) of a plane is TMA-loaded INTO the plane's output
+                     // staging buffer two planes ahead (maps.side) and transformed in place; needs 3 staging buffers per group
   long long* dbg;    // optional timeline buffer [3 roles][32 tiles][4] of clock64 stamps written by CTA 0 (tuning aid)
 };
 #define EPI_STAMP(idx) \
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
   uint64_t* acc_full = b_empty + Cfg::NB_MAX;
   uint64_t* acc_empty = acc_full + Cfg::NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::NACC);
+  uint64_t* side_full = reinterpret_cast<uint64_t*>(aux + 768);   // [6]: one per staging buffer in side-ring mode
   float* s_stats = reinterpret_cast<float*>(aux + 1024);
   float4* s_coef = reinterpret_cast<float4*>(aux + 1024 + 8 * BN * 8);
 
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       for (int s = 0; s < Cfg::NHALO; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], NI); }
       for (int s = 0; s < Cfg::NB_MAX; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
       for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], NI); mbar_init(&acc_empty[s], 8); }
+      for (int s = 0; s < 6; ++s) mbar_init(&side_full[s], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -162,14 +167,6 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       fast_divmod(t, hp.fd_d, n, dt);
       const int w0 = wt * 8, h0 = ht * 16, d0 = dt * TD, n0 = nt * BN;
       if (halo_role) HALO_STAMP(0, 0);
-      if (halo_role && hp.side_pf) {
-        // the epilogue reads one row of the side input (residual / GroupNorm input) per thread and plane straight from global
-        // memory, one plane ahead at most (registers): from HBM that latency bounded the drain (~4.1 K cycles per plane of
-        // 128 x 64 in the GroupNorm-backward epilogue, profiles/r02_halo_timeline.txt).  This warp runs 1-3 tiles ahead of
-        // the epilogue: it asks the TMA unit to pull the tile's side planes into L2 now, so those loads become L2 hits.
-        for (int dpl = 0; dpl < TD; ++dpl)
-          if (d0 + dpl < p.Do) tma_prefetch_l2_5d_if(issue, &maps.side, n0, w0, h0, d0 + dpl, n);
-      }
       for (int g = 0; g < groups0 + groups1; ++g) {
         const int src = g < groups0 ? 0 : 1;
         const int kc = src == 0 ? g : g - groups0;
@@ -396,6 +393,37 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     const int side_ld = mode == 0 ? p.ldr : p.ldx;
     double* stat_dst = (mode == 0) ? p.stats : p.bstats;
     const int stat_ld = (mode == 0) ? p.stats_ld : p.coef_ld;
+    // Side-ring mode (lean variants with a side input; the host dispatches the generic variant when the three staging buffers
+    // per group do not fit).  The side rows used to be read by every thread straight from global memory into registers, one
+    // plane ahead at most: the ncu source view of the 32->64 GroupNorm-backward launch (profiles/r02_halo_mode1_source.txt) put
+    // 15 % of ALL samples on the first instruction that waits for those loads and 11 % on the group barrier behind it.  Now
+    // the group's issuing thread TMA-loads the side tile of the plane two planes ahead INTO that plane's output staging
+    // buffer (same box and swizzle as the store), the threads transform their own 16-byte chunks in place, and the buffer
+    // is TMA-stored: no registers, no per-thread global loads, ~1.5 plane times of latency cover.
+    const bool ring = EV != 0 && side_hi != nullptr;
+    const int ppg = COLS ? TD : (TD - grp + 1) / 2;      // planes of one tile this group drains
+    const int sbar0 = COLS ? 0 : grp * 3;                // this group's side_full barriers (one per staging buffer)
+    auto issue_side = [&](uint32_t q) {                  // issuing thread: request plane q of the group's plane sequence
+      const int tq = (int)(q / (uint32_t)ppg), kk = (int)(q % (uint32_t)ppg);
+      const long long tl = (long long)blockIdx.x + (long long)tq * gridDim.x;
+      if (tl >= hp.tiles_total) return;
+      int t = (int)tl, nt, wt, ht, dt, n;
+      fast_divmod(t, hp.fd_nt, t, nt);
+      fast_divmod(t, hp.fd_w, t, wt);
+      fast_divmod(t, hp.fd_h, t, ht);
+      fast_divmod(t, hp.fd_d, n, dt);
+      const int d = dt * TD + (COLS ? 0 : grp) + kk * pstep;     // may lie beyond Do: the box then reads as zeros
+      uint8_t* dst = smem_out + ((COLS ? 0 : grp * nog) + (q % 3u)) * out_buf_bytes;
+      uint64_t* bar = &side_full[sbar0 + (q % 3u)];
+      int nbx = 0;
+#pragma unroll
+      for (int cb = 0; cb < Cfg::NBO; ++cb) nbx += (nt * BN + cb * Cfg::CBO < p.Cout) ? 1 : 0;
+      mbar_expect_tx(bar, nbx * Cfg::OUT_BOX);
+#pragma unroll
+      for (int cb = 0; cb < Cfg::NBO; ++cb)
+        if (nt * BN + cb * Cfg::CBO < p.Cout)
+          tma_load_5d(dst + cb * Cfg::OUT_BOX, &maps.side, bar, nt * BN + cb * Cfg::CBO, wt * 8, ht * 16, d, n);
+    };
     float rs[NACCUM], rq[NACCUM];
 #pragma unroll
     for (int i = 0; i < NACCUM; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
@@ -438,17 +466,20 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     // side-input rows of chunk group sg (SG chunks of 16 channels) of the voxel row at vx
     uint4 sh[2 * SG], sl[2 * SG];
     auto load_side = [&](long long vx, int n0, int sg, bool ok) {
-      if (!side_hi || !ok) return;
+      if constexpr (EV == 0) {                       // lean variants: side ring (above)
+        if (!side_hi || !ok) return;
 #pragma unroll
-      for (int c = 0; c < 2 * SG; ++c) {
-        const int cc = n0 + (jb + sg * SG) * 16 + c * 8;
-        if (cc < p.Cout) {
-          sh[c] = *reinterpret_cast<const uint4*>(side_hi + vx * side_ld + cc);
-          if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vx * side_ld + cc);
+        for (int c = 0; c < 2 * SG; ++c) {
+          const int cc = n0 + (jb + sg * SG) * 16 + c * 8;
+          if (cc < p.Cout) {
+            sh[c] = *reinterpret_cast<const uint4*>(side_hi + vx * side_ld + cc);
+            if (side_lo) sl[c] = *reinterpret_cast<const uint4*>(side_lo + vx * side_ld + cc);
+          }
         }
       }
     };
 
+    if (ring && threadIdx.x == issuer && ppg > 0) { issue_side(0); issue_side(1); }
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       EPI_STAMP(40);
       int t = tile;
@@ -504,6 +535,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
           if (threadIdx.x == issuer) tma_store_wait_read0();
           group_sync();
         }
+        if (ring) mbar_wait(&side_full[sbar0 + oi % 3u], (oi / 3u) & 1u);   // this plane's side tile sits in `stage`
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
           const int j = jb + jj;
@@ -525,6 +557,9 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const int cc = c0 + hf * 8;
+              // the 8 channels (16 bytes) of this row in the staging tile: box (cc - n0) / CBO, chunk within the box row
+              const int cb = (j * 16 + hf * 8) / Cfg::CBO, cchunk = ((j * 16 + hf * 8) % Cfg::CBO) / 8;
+              uint8_t* dst = stage + cb * Cfg::OUT_BOX + stage_off<Cfg::CBO>(row, cchunk);
               float vv[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) vv[i] = 0.f;
@@ -533,7 +568,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[hf * 8 + i]);
                 if (side_hi) {
-                  const uint4 a = sh[(jj % SG) * 2 + hf];
+                  const uint4 a = EV != 0 ? *reinterpret_cast<const uint4*>(dst) : sh[(jj % SG) * 2 + hf];
                   sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
                   sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
                   if (side_lo) {
@@ -573,12 +608,9 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
                   }
                 }
               }
-              // stage the 8 channels (16 bytes) of this row: box (cc - n0) / CBO, chunk within the box row
               uint4 o;
               o.x = pack_bf16x2(vv[0], vv[1]); o.y = pack_bf16x2(vv[2], vv[3]);
               o.z = pack_bf16x2(vv[4], vv[5]); o.w = pack_bf16x2(vv[6], vv[7]);
-              const int cb = (j * 16 + hf * 8) / Cfg::CBO, cchunk = ((j * 16 + hf * 8) % Cfg::CBO) / 8;
-              uint8_t* dst = stage + cb * Cfg::OUT_BOX + stage_off<Cfg::CBO>(row, cchunk);
               *reinterpret_cast<uint4*>(dst) = o;
               if (split) {
                 uint4 l;
@@ -595,6 +627,12 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
               for (int i = 0; i < 16; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
             }
           }
+          if (ring && jj == 0 && threadIdx.x == issuer) {
+            // buffer (oi + 2) % 3 was stored from at the end of the previous plane: once that store has read it, the side tile of
+            // the plane two ahead can land there
+            tma_store_wait_read0();
+            issue_side(oi + 2);
+          }
           // the registers of this side-input group are consumed: request the next group (this plane's, else the next plane's)
           if ((jj % SG) == SG - 1) {
             if (jj / SG + 1 < NSG) load_side(vox, n0, jj / SG + 1, valid);
@@ -605,7 +643,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
         EPI_STAMP(dpl * 8 + 2);
         fence_proxy_async();
         EPI_STAMP(dpl * 8 + 3);
-        if (nog > 1 && threadIdx.x == issuer) tma_store_wait_read0();   // the other buffer is free again after the barrier
+        if (!ring && nog > 1 && threadIdx.x == issuer) tma_store_wait_read0();   // the other buffer is free again after the barrier
         EPI_STAMP(dpl * 8 + 4);
         group_sync();
         EPI_STAMP(dpl * 8 + 5);
@@ -652,6 +690,10 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
     const int v = atoi(e);
     if (Cfg::COLSPLIT) { if (v == 1 || v == 2) h.nout = v; }   // shared ring of 1 or 2
     else if (v == 2 || v == 4) h.nout = v;                      // 1 or 2 per plane-split group
+  }
+  if (h.side_ring) {   // side-ring mode: three staging buffers per epilogue group, and still >= 3 weight stages
+    h.nout = Cfg::COLSPLIT ? 3 : 6;
+    if ((rem - h.nout * out_buf) / Cfg::B_BYTES < 3) return HALO_NO_RING;   // the caller falls back to the generic variant
   }
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;
