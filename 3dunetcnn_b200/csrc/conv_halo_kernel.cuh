@@ -459,7 +459,12 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       if ((lane & 1) == 0) {
         const int col = j * 16 + ((lane >> 1) & 15);
         float2 acc = s_mine[col];
-        acc.x += s1; acc.y += s2;
+        if constexpr (EV == 2) {   // raw sum(dz * x) -> sum(dz * xhat) with this run's (mean, rstd) of the channel
+          const float* f = reinterpret_cast<const float*>(s_coef) + (col >> 1) * 8 + (col & 1);
+          acc.x += s1; acc.y += f[6] * (s2 - f[4] * s1);
+        } else {
+          acc.x += s1; acc.y += s2;
+        }
         s_mine[col] = acc;
       }
     };
@@ -499,8 +504,16 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
         }
         if (mode == 1) {
           asm volatile("bar.sync 3, 256;" ::: "memory");   // nobody still reads the old coefficients
-          for (int c = e; c < BN; c += 256)
-            s_coef[c] = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = e; c < BN; c += 256) {
+            const float4 k = (n0 + c < p.Cout) ? p.coef[(long long)n * p.coef_ld + n0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EV == 2) {
+              // pair-interleaved for the packed f32x2 arithmetic: channel pair q = c / 2 holds [a0 a1 b0 b1 | mean0 mean1 rstd0 rstd1]
+              float* f = reinterpret_cast<float*>(s_coef) + (c >> 1) * 8 + (c & 1);
+              f[0] = k.x; f[2] = k.y; f[4] = k.z; f[6] = k.w;
+            } else {
+              s_coef[c] = k;
+            }
+          }
           asm volatile("bar.sync 3, 256;" ::: "memory");
         }
         cur_n = n; cur_n0 = n0;
@@ -596,6 +609,22 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
                   }
 #pragma unroll
                   for (int i = 0; i < 8; ++i) { as_[hf * 8 + i] += vv[i]; aq_[hf * 8 + i] = fmaf(vv[i], vv[i], aq_[hf * 8 + i]); }
+                } else if constexpr (EV == 2) {
+                  // packed f32x2 arithmetic on channel pairs; the second statistic is accumulated as the RAW sum(dz * x) and
+                  // centred / scaled once per run in reduce_chunk: sum(dz * xhat) = rstd * (sum(dz * x) - mean * sum(dz))
+#pragma unroll
+                  for (int i = 0; i < 8; i += 2) {
+                    const float4 ab = s_coef[(j * 16 + hf * 8 + i)];          // [a_i a_i+1 b_i b_i+1] (pair-interleaved, see above)
+                    const float2 x2 = make_float2(sv[i], sv[i + 1]);
+                    const float2 z2 = __ffma2_rn(make_float2(ab.x, ab.y), x2, make_float2(ab.z, ab.w));
+                    const float2 m2 = make_float2(z2.x > 0.f ? 1.f : p.slope, z2.y > 0.f ? 1.f : p.slope);
+                    const float2 dz2 = __fmul2_rn(make_float2(vv[i], vv[i + 1]), m2);
+                    vv[i] = dz2.x; vv[i + 1] = dz2.y;
+                    const float2 s2 = __fadd2_rn(make_float2(as_[hf * 8 + i], as_[hf * 8 + i + 1]), dz2);
+                    as_[hf * 8 + i] = s2.x; as_[hf * 8 + i + 1] = s2.y;
+                    const float2 q2 = __ffma2_rn(dz2, x2, make_float2(aq_[hf * 8 + i], aq_[hf * 8 + i + 1]));
+                    aq_[hf * 8 + i] = q2.x; aq_[hf * 8 + i + 1] = q2.y;
+                  }
                 } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {

@@ -143,9 +143,14 @@ class DevicePrefetcher:
     side stream while the current step computes (the reference copies synchronously from pageable memory on the compute
     stream: training_utils.py:89-91).  Pageable tensors still work, they just do not overlap."""
 
+    _streams = {}    # one copy stream per device, kept across epochs (stream creation is not free)
+
     def __init__(self, loader, device):
         self.loader, self.device = loader, device
-        self.stream = torch.cuda.Stream(device=device)
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=device)
+        self.stream = DevicePrefetcher._streams[key]
 
     def __len__(self):
         return len(self.loader)
@@ -183,9 +188,13 @@ class _LaggedLoss:
     """Reads step i's loss while step i+1 is already queued: an async D2H into pinned memory + an event per step
     instead of ``loss.item()`` right after the launch (training_utils.py:63), which would drain the GPU every step."""
 
+    _pinned = None   # the two pinned read-back slots and their events are process-wide: cudaHostAlloc per epoch is not free
+
     def __init__(self):
-        self.slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        if _LaggedLoss._pinned is None:
+            _LaggedLoss._pinned = ([torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)],
+                                   [torch.cuda.Event(), torch.cuda.Event()])
+        self.slots, self.events = _LaggedLoss._pinned
         self.pending = []   # (slot, batch_size)
         self.i = 0
 
