@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
     // is TMA-stored: no registers, no per-thread global loads, ~1.5 plane times of latency cover.
     const bool ring = EV != 0 && side_hi != nullptr;
     const int ppg = COLS ? TD : (TD - grp + 1) / 2;      // planes of one tile this group drains
-    const int sbar0 = COLS ? 0 : grp * 3;                // this group's side_full barriers (one per staging buffer)
+    const int sbar0 = COLS ? 0 : grp * 3;                // this group's side_full barriers (one per staging buffer, <= 3)
     auto issue_side = [&](uint32_t q) {                  // issuing thread: request plane q of the group's plane sequence
       const int tq = (int)(q / (uint32_t)ppg), kk = (int)(q % (uint32_t)ppg);
       const long long tl = (long long)blockIdx.x + (long long)tq * gridDim.x;
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       fast_divmod(t, hp.fd_h, t, ht);
       fast_divmod(t, hp.fd_d, n, dt);
       const int d = dt * TD + (COLS ? 0 : grp) + kk * pstep;     // may lie beyond Do: the box then reads as zeros
-      uint8_t* dst = smem_out + ((COLS ? 0 : grp * nog) + (q % 3u)) * out_buf_bytes;
-      uint64_t* bar = &side_full[sbar0 + (q % 3u)];
+      uint8_t* dst = smem_out + ((COLS ? 0 : grp * nog) + (q % (uint32_t)nog)) * out_buf_bytes;
+      uint64_t* bar = &side_full[sbar0 + (q % (uint32_t)nog)];
       int nbx = 0;
 #pragma unroll
       for (int cb = 0; cb < Cfg::NBO; ++cb) nbx += (nt * BN + cb * Cfg::CBO < p.Cout) ? 1 : 0;
@@ -484,7 +484,11 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
       }
     };
 
-    if (ring && threadIdx.x == issuer && ppg > 0) { issue_side(0); issue_side(1); }
+    // look-ahead = buffers per group - 1: two planes with three buffers; one plane with two (configurations whose three-box
+    // weight stages leave no room for a third buffer)
+    const uint32_t la = (uint32_t)nog - 1u;
+    if (ring && threadIdx.x == issuer && ppg > 0)
+      for (uint32_t q = 0; q < la; ++q) issue_side(q);
     for (int tile = blockIdx.x; tile < hp.tiles_total; tile += gridDim.x, ++ti) {
       EPI_STAMP(40);
       int t = tile;
@@ -548,7 +552,7 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
           if (threadIdx.x == issuer) tma_store_wait_read0();
           group_sync();
         }
-        if (ring) mbar_wait(&side_full[sbar0 + oi % 3u], (oi / 3u) & 1u);   // this plane's side tile sits in `stage`
+        if (ring) mbar_wait(&side_full[sbar0 + oi % (uint32_t)nog], (oi / (uint32_t)nog) & 1u);   // this plane's side tile sits in `stage`
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
           const int j = jb + jj;
@@ -657,10 +661,10 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
             }
           }
           if (ring && jj == 0 && threadIdx.x == issuer) {
-            // buffer (oi + 2) % 3 was stored from at the end of the previous plane: once that store has read it, the side tile of
-            // the plane two ahead can land there
+            // buffer (oi + la) % nog was stored from at the end of the previous plane: once that store has read it, the side tile
+            // of the plane `la` ahead can land there
             tma_store_wait_read0();
-            issue_side(oi + 2);
+            issue_side(oi + la);
           }
           // the registers of this side-input group are consumed: request the next group (this plane's, else the next plane's)
           if ((jj % SG) == SG - 1) {
@@ -720,9 +724,12 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
     if (Cfg::COLSPLIT) { if (v == 1 || v == 2) h.nout = v; }   // shared ring of 1 or 2
     else if (v == 2 || v == 4) h.nout = v;                      // 1 or 2 per plane-split group
   }
-  if (h.side_ring) {   // side-ring mode: three staging buffers per epilogue group, and still >= 3 weight stages
-    h.nout = Cfg::COLSPLIT ? 3 : 6;
-    if ((rem - h.nout * out_buf) / Cfg::B_BYTES < 3) return HALO_NO_RING;   // the caller falls back to the generic variant
+  if (h.side_ring) {   // side-ring mode: three staging buffers per epilogue group (two-plane look-ahead) and still >= 3 weight
+    h.nout = Cfg::COLSPLIT ? 3 : 6;     // stages; else two per group (one-plane look-ahead) for the plane-split tiles
+    if ((rem - h.nout * out_buf) / Cfg::B_BYTES < 3) {
+      h.nout = 4;
+      if (Cfg::COLSPLIT || (rem - h.nout * out_buf) / Cfg::B_BYTES < 3) return HALO_NO_RING;   // the caller falls back
+    }
   }
   int nb = (rem - h.nout * out_buf) / Cfg::B_BYTES;
   if (nb > Cfg::NB_MAX) nb = Cfg::NB_MAX;

@@ -51,7 +51,7 @@ CONFIGS = {
 
 # mean DRAM bytes per k_conv_halo launch in one C2 training step (ncu launch list under profiles/); refresh with
 # tools/gpu_trip_prof.sh + tools/summarize_ncu.py when the kernel or the dispatch changes
-NCU_TRAFFIC = {"bytes_per_launch": 358.5e6, "source": "profiles/r01_final_launches.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+NCU_TRAFFIC = {"bytes_per_launch": 339.6e6, "source": "profiles/r02_launches.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
                                                       "mean over the kernel's launches of one C2 step)"}
 
 
