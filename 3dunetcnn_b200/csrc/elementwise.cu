@@ -803,10 +803,104 @@ __global__ void k_upsample2x_bwd(Act dy, Act dx) {
   }
 }
 
+// Register-blocked form (single-pass bf16, even extents): a thread owns a 2 x 2 x 2 block of dx voxels (8 channels) and walks the
+// 6 x 6 x 6 neighbourhood of dy once -- 216 16-byte loads per 8 outputs instead of 8 x 64: the gather form above is bound by
+// L1/L2 load bandwidth (8x read amplification), not by HBM.  Per axis, block m (outputs 2m, 2m+1) meets dy indices 4m-1+i,
+// i = 0..5: output 2m with weights (.25 .75 .75 .25) on i = 0..3, output 2m+1 with the same on i = 2..5; a neighbour outside
+// the volume hands its weight to the clamped one (i = 0 when m = 0, i = 5 at the far end).
+__device__ __forceinline__ float blk_w0(int i, bool first) {
+  return i == 0 ? (first ? 0.f : 0.25f) : i == 1 ? (first ? 1.0f : 0.75f) : i == 2 ? 0.75f : i == 3 ? 0.25f : 0.f;
+}
+__device__ __forceinline__ float blk_w1(int i, bool last) {
+  return i == 2 ? 0.25f : i == 3 ? 0.75f : i == 4 ? (last ? 1.0f : 0.75f) : i == 5 ? (last ? 0.f : 0.25f) : 0.f;
+}
+
+__global__ void __launch_bounds__(128) k_upsample2x_bwd_blk(Act dy, Act dx) {
+  const int c8n = dx.C / 8;
+  const int bw = dx.W >> 1, bh = dx.H >> 1, bd = dx.D >> 1;
+  const long long total = (long long)dx.N * bd * bh * bw * c8n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    long long v = t / c8n;
+    const int mw = (int)(v % bw); v /= bw;
+    const int mh = (int)(v % bh); v /= bh;
+    const int md = (int)(v % bd);
+    const int n = (int)(v / bd);
+    const bool fw = mw == 0, lw = mw == bw - 1, fh = mh == 0, lh = mh == bh - 1, fd = md == 0, ld_ = md == bd - 1;
+    float wx0[4], wx1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { wx0[i] = blk_w0(i, fw); wx1[i] = blk_w1(i + 2, lw); }
+    float o[2][2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[a][b][c][j] = 0.f;
+    const bf16* base = dy.hi + (long long)n * dy.D * dy.H * dy.W * dy.ld + c8 * 8;
+#pragma unroll 1
+    for (int iz = 0; iz < 6; ++iz) {
+      const float wz0 = blk_w0(iz, fd), wz1 = blk_w1(iz, ld_);
+      if (wz0 == 0.f && wz1 == 0.f) continue;           // the plane lies outside the volume
+      const int gz = 4 * md - 1 + iz;
+#pragma unroll 1
+      for (int iy = 0; iy < 6; ++iy) {
+        const float wy0 = blk_w0(iy, fh), wy1 = blk_w1(iy, lh);
+        if (wy0 == 0.f && wy1 == 0.f) continue;
+        const int gy = 4 * mh - 1 + iy;
+        const bf16* row = base + (((long long)gz * dy.H + gy) * dy.W + 4 * mw - 1) * dy.ld;
+        float r0[8], r1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r0[j] = 0.f; r1[j] = 0.f; }
+#pragma unroll
+        for (int ix = 0; ix < 6; ++ix) {
+          if ((ix == 0 && fw) || (ix == 5 && lw)) continue;
+          const uint4 a = *reinterpret_cast<const uint4*>(row + (long long)ix * dy.ld);
+          float g[8];
+          g[0] = bf16_lo_to_f(a.x); g[1] = bf16_hi_to_f(a.x); g[2] = bf16_lo_to_f(a.y); g[3] = bf16_hi_to_f(a.y);
+          g[4] = bf16_lo_to_f(a.z); g[5] = bf16_hi_to_f(a.z); g[6] = bf16_lo_to_f(a.w); g[7] = bf16_hi_to_f(a.w);
+          if (ix < 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r0[j] = fmaf(wx0[ix], g[j], r0[j]);
+          }
+          if (ix >= 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r1[j] = fmaf(wx1[ix - 2], g[j], r1[j]);
+          }
+        }
+        const float w00 = wz0 * wy0, w01 = wz0 * wy1, w10 = wz1 * wy0, w11 = wz1 * wy1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[0][0][0][j] = fmaf(w00, r0[j], o[0][0][0][j]); o[0][0][1][j] = fmaf(w00, r1[j], o[0][0][1][j]);
+          o[0][1][0][j] = fmaf(w01, r0[j], o[0][1][0][j]); o[0][1][1][j] = fmaf(w01, r1[j], o[0][1][1][j]);
+          o[1][0][0][j] = fmaf(w10, r0[j], o[1][0][0][j]); o[1][0][1][j] = fmaf(w10, r1[j], o[1][0][1][j]);
+          o[1][1][0][j] = fmaf(w11, r0[j], o[1][1][0][j]); o[1][1][1][j] = fmaf(w11, r1[j], o[1][1][1][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          store8(dx.hi, nullptr, ((((long long)n * dx.D + 2 * md + a) * dx.H + 2 * mh + b) * dx.W + 2 * mw + c) * dx.ld + c8 * 8, o[a][b][c]);
+  }
+}
+
 int launch_upsample2x_bwd(const Act& dy, const Act& dx, cudaStream_t st) {
   B200_REQUIRE(dx.C % 8 == 0 && dy.C == dx.C, E_INVALID, "upsample_bwd: channel mismatch");
   B200_REQUIRE(dy.D == 2 * dx.D && dy.H == 2 * dx.H && dy.W == 2 * dx.W, E_UNSUPPORTED, "upsample_bwd: not 2x");
   if (use_tiled_upsample_bwd()) return launch_upsample2x_bwd_tiled(dy, dx, st);
+  static const bool no_blk = getenv("B200UNET_UPSAMPLE_BWD_GATHER") != nullptr;   // A/B switch: the one-voxel-per-thread gather form
+  if (!no_blk && !dy.lo && !dx.lo && dx.D % 2 == 0 && dx.H % 2 == 0 && dx.W % 2 == 0 && dx.D >= 2 && dx.H >= 2 && dx.W >= 2) {
+    const long long blocks = (long long)dx.N * (dx.D / 2) * (dx.H / 2) * (dx.W / 2) * (dx.C / 8);
+    k_upsample2x_bwd_blk<<<ew_blocks(blocks, 128), 128, 0, st>>>(dy, dx);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return OK;
+  }
   long long total = dx.voxels() * (dx.C / 8);
   k_upsample2x_bwd<<<ew_blocks(total, 256), 256, 0, st>>>(dy, dx);
   B200_CHECK_CUDA(cudaGetLastError());

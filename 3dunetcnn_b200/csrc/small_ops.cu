@@ -75,18 +75,35 @@ __device__ __forceinline__ void pack_job_tiled(float (&tile)[PT][PT + 1][PTT], c
       }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < PT * PT * T; idx += blockDim.x) {
-      const int t = idx / (PT * PT), rem = idx % (PT * PT);
+    // write phase: one 16-byte store (8 bf16 along the destination's inner channel axis) per thread and step; padded channel
+    // counts are multiples of 8 and the tile origin of 16, so a chunk is either wholly inside the padded extent or skipped
+    for (int idx = threadIdx.x; idx < PT * 2 * T; idx += blockDim.x) {
+      const int t = idx / (PT * 2), rem = idx % (PT * 2), outer = rem >> 1, half = (rem & 1) * 8;
       const int ts = flip ? T - 1 - t : t;
-      int col, cil;
+      float v[8];
       long long dst;
-      if (!co_inner) { col = rem / PT; cil = rem % PT; dst = ((long long)t * j.Cop + co0 + col) * j.Cip + ci0 + cil; }
-      else           { cil = rem / PT; col = rem % PT; dst = ((long long)t * j.Cip + ci0 + cil) * j.Cop + co0 + col; }
-      if (co0 + col >= j.Cop || ci0 + cil >= j.Cip) continue;
-      const float v = tile[col][cil][ts];
-      const bf16 h = __float2bfloat16_rn(v);
-      hi[dst] = h;
-      if (lo) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+      if (!co_inner) {   // [T][Cop][Cip]: outer = co, chunk along ci
+        if (co0 + outer >= j.Cop || ci0 + half >= j.Cip) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = tile[outer][half + q][ts];
+        dst = ((long long)t * j.Cop + co0 + outer) * j.Cip + ci0 + half;
+      } else {           // [T][Cip][Cop]: outer = ci, chunk along co
+        if (ci0 + outer >= j.Cip || co0 + half >= j.Cop) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = tile[half + q][outer][ts];
+        dst = ((long long)t * j.Cip + ci0 + outer) * j.Cop + co0 + half;
+      }
+      uint4 a;
+      a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(hi + dst) = a;
+      if (lo) {
+        uint4 b;
+        b.x = pack_bf16x2(v[0] - bf16_lo_to_f(a.x), v[1] - bf16_hi_to_f(a.x));
+        b.y = pack_bf16x2(v[2] - bf16_lo_to_f(a.y), v[3] - bf16_hi_to_f(a.y));
+        b.z = pack_bf16x2(v[4] - bf16_lo_to_f(a.z), v[5] - bf16_hi_to_f(a.z));
+        b.w = pack_bf16x2(v[6] - bf16_lo_to_f(a.w), v[7] - bf16_hi_to_f(a.w));
+        *reinterpret_cast<uint4*>(lo + dst) = b;
+      }
     }
   }
 }

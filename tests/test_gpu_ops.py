@@ -343,7 +343,7 @@ def test_groupnorm_relu_forward_backward(pkg, C, G, dims, split):
 
 
 @pytest.mark.parametrize("split", [False, True])
-@pytest.mark.parametrize("dims", [(4, 6, 8), (3, 5, 7), (1, 2, 4)])
+@pytest.mark.parametrize("dims", [(4, 6, 8), (3, 5, 7), (1, 2, 4), (2, 2, 6)])   # even extents: register-blocked adjoint; (2, ..): first == last block
 def test_trilinear_upsample_forward_backward(pkg, dims, split):
     L = pkg.lib
     torch.manual_seed(5)
