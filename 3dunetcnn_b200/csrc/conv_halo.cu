@@ -190,18 +190,20 @@ int launch_conv_halo(const ConvOp& op_in, int num_sms, cudaStream_t st) {
   // (The round-1 experiment with two issuing warps and private accumulator sets, NI = 2, ran correctly but slower than
   //  either variant -- 0.38 vs 0.30 ms on 32->32+residual -- and is no longer instantiated.)
   const bool side_input = op.res != nullptr || op.mode == 1;
+  // epilogue variant: the lean bodies when none of the rare options is in play
+  static const bool no_lean = getenv("B200UNET_HALO_GENERIC_EPILOGUE") != nullptr;   // A/B switch
+  const bool lean = !no_lean && !split && !op.scale && !op.bias && !op.zero_last && !(no_ring && side && side->hi);
   int kws = 1;
   if (BN <= 32 && (tpb * BN * KC * 2) % 1024 == 0 && KC == 32) {
-    if (a.kchunks[0] >= 2 || BN < 32 || !side_input) kws = 3;
+    // with the side ring (lean variants) the three-box stages also win on side-input layers: 32->32 GroupNorm-backward
+    // 0.285 -> 0.246 ms (profiles/r02_layer_times_kws3_ab.txt); the generic variant's register-staged side rows keep the old rule
+    if (a.kchunks[0] >= 2 || BN < 32 || !side_input || lean) kws = 3;
   }
   if (const char* e = getenv("B200UNET_HALO_KWS")) {   // tuning override (1 or 3)
     const int v = atoi(e);
     if (v == 1 || (v == 3 && BN <= 32 && (tpb * BN * KC * 2) % 1024 == 0)) kws = v;
   }
   if (kws == 3 && !halo_fits(KC, BN, TD, split, 3)) kws = 1;
-  // epilogue variant: the lean bodies when none of the rare options is in play
-  static const bool no_lean = getenv("B200UNET_HALO_GENERIC_EPILOGUE") != nullptr;   // A/B switch
-  const bool lean = !no_lean && !split && !op.scale && !op.bias && !op.zero_last && !(no_ring && side && side->hi);
   if (lean) {
     h.side_ring = (side && side->hi) ? 1 : 0;
     int rc = op.mode == 0 ? launch_halo_ev1(KC, BN, TD, kws, maps, a, h, grid, st) : launch_halo_ev2(KC, BN, TD, kws, maps, a, h, grid, st);

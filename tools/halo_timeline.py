@@ -29,6 +29,14 @@ if mode == "mode1":
 for _ in range(3):
     L.conv3d(x, whi, wlo, 3, 1, y, cop, cip, **kw)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+os.environ.pop("B200UNET_HALO_DBG")          # time it without the stamps
+e0.record()
+for _ in range(5):
+    L.conv3d(x, whi, wlo, 3, 1, y, cop, cip, **kw)
+e1.record()
+torch.cuda.synchronize()
+print("kernel time without stamps: %.4f ms per launch" % (e0.elapsed_time(e1) / 5))
 ep = dbg.cpu()[384:]
 d = dbg.cpu()[:384].view(3, 32, 4)
 t0 = int(d[0, 0, 0])
@@ -37,6 +45,7 @@ print("tile | prod: start, halo_empty_ok | mma: start, acc_empty_ok, halo_full_o
 for t in range(12):
     f = lambda v: "%7d" % (int(v) - t0) if int(v) else "      -"
     print("%4d | %s %s | %s %s %s %s | %s %s %s %s" % ((t,) + tuple(f(v) for v in list(d[0, t, :2]) + list(d[1, t]) + list(d[2, t]))))
+print("MMA commit-to-commit deltas of tiles 12..31:", [int(d[1, t, 3]) - int(d[1, t - 1, 3]) for t in range(12, 32) if int(d[1, t, 3])])
 per = (int(d[1, 11, 3]) - int(d[1, 3, 3])) / 8.0
 print("steady-state cycles per tile (MMA commit to commit): %.0f ; epilogue drain time per tile: %.0f" % (per, float((d[2, 3:11, 2] - d[2, 3:11, 1]).double().mean())))
 
