@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200UNET_LIB: load a differently-built copy of the library (A/B runs of compile-time kernel variants: tools/gpu_experiments.sh)
+# B200UNET_LIB: load a differently-built copy of the library (A/B runs of compile-time kernel variants: `make BUILD=... OUT=... EXTRA=-D...` in csrc/)
 LIB_PATH = os.environ.get("B200UNET_LIB") or os.path.join(_HERE, "libb200unet.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "b200unet.h")
