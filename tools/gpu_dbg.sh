@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | grep "smoke\|worst" | tail -9
-echo "--- gather upsample adjoint"; B200UNET_UPSAMPLE_BWD_GATHER=1 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | grep "smoke\|worst" | tail -5
-echo "--- old small ops"; B200UNET_OLD_SMALL_OPS=1 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | grep "smoke\|worst" | tail -5
-echo "--- kws 1"; B200UNET_HALO_KWS=1 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | grep "smoke\|worst" | tail -5
+TAG=${1:-r02s}
+timeout 600 ncu --set full --import-source on --clock-control none -k "regex:k_igemm_conv<32, 32>" -s 2 -c 2 -f -o gpurun_out/${TAG}_igemm_32_32 python tools/prof_step.py 2 > gpurun_out/ncu_cls.log 2>&1; tail -2 gpurun_out/ncu_cls.log
+ls -la gpurun_out/${TAG}_igemm_32_32.ncu-rep
