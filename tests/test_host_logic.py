@@ -267,3 +267,42 @@ def test_tile_decode_fast_division_restatement():
         for x in list(range(0, 600)) + [rnd.randrange(0, 2 ** 31) for _ in range(300)] + [2 ** 31 - 1]:
             q = (((x * mul) >> 32) >> shr) if d > 1 else x
             assert q == x // d and x - q * d == x % d
+
+
+@pytest.mark.parametrize("n", [2, 4, 6, 10])
+def test_register_blocked_trilinear_adjoint_weights(n):
+    """elementwise.cu:k_upsample2x_bwd_blk: per axis, block m (outputs 2m, 2m+1) meets dy indices 4m-1+i, i = 0..5, with the
+    weights blk_w0 / blk_w1.  Restated here and held to the transpose of the oracle's 1-D upsampling matrix."""
+    import numpy as np
+
+    def blk_w0(i, first):
+        return {0: 0.0 if first else 0.25, 1: 1.0 if first else 0.75, 2: 0.75, 3: 0.25}.get(i, 0.0)
+
+    def blk_w1(i, last):
+        return {2: 0.25, 3: 0.75, 4: 1.0 if last else 0.75, 5: 0.0 if last else 0.25}.get(i, 0.0)
+
+    # 1-D upsampling matrix U (2n x n) from the oracle: column k = upsampled unit vector e_k along the last axis
+    U = np.zeros((2 * n, n))
+    for k in range(n):
+        e = np.zeros((1, 1, 1, 1, n))
+        e[..., k] = 1.0
+        U[:, k] = _up_last_axis(e)
+    A = np.zeros((n, 2 * n))      # the kernel's adjoint
+    for m in range(n // 2):
+        first, last = m == 0, m == n // 2 - 1
+        for i in range(6):
+            g = 4 * m - 1 + i
+            w0, w1 = blk_w0(i, first), blk_w1(i, last)
+            if w0 == 0.0 and w1 == 0.0:
+                continue
+            assert 0 <= g < 2 * n, (m, i)
+            A[2 * m, g] += w0
+            A[2 * m + 1, g] += w1
+    assert np.allclose(A, U.T, atol=1e-12)
+
+
+def _up_last_axis(e):
+    """the oracle's trilinear x2 restricted to the last axis: upsample a (1,1,1,1,n) array and undo the two unit axes"""
+    from oracle import trilinear_upsample2x
+    y = trilinear_upsample2x(e)            # (1, 1, 2, 2, 2n): the unit axes are replicated, the last axis is interpolated
+    return y[0, 0, 0, 0, :]
