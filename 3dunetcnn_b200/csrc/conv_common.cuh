@@ -135,7 +135,7 @@ template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t tacc, int lane_base, int lane, int n,
                                                    int n0, long long vox, bool valid, float* s_stats,
                                                    const float4* s_coef, bool want_stats, bool edge, uint8_t* stage,
-                                                   int row, bool split, const uint4* pre_side = nullptr) {
+                                                   int row, bool split) {
   // `stage`: 1024-aligned shared staging tile [BN/CBO boxes][128 rows][CBO channels] (+ the lo tile OUT_TILE bytes
   // later in split mode); the caller TMA-stores it after a proxy fence + barrier.
   constexpr int G = BN < 64 ? BN : 64;
@@ -149,12 +149,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t t
   for (int g0 = 0; g0 < BN; g0 += G) {
     if (n0 + g0 >= p.Cout) break;
     uint4 ph[G / 8], pl[G / 8];
-    // pre_side (BN <= 64, single-pass bf16): the caller has already loaded this tile's side rows (software pipelining across
-    // the parity classes of the streaming kernel)
-    if (pre_side) {
-#pragma unroll
-      for (int i = 0; i < G / 8; ++i) ph[i] = pre_side[i];
-    } else if (side_hi && valid) {
+    if (side_hi && valid) {
 #pragma unroll
       for (int i = 0; i < G / 8; ++i) {
         const int cc = n0 + g0 + i * 8;
@@ -186,7 +181,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, uint32_t t
               const uint4 a = ph[jj * 2 + hf];
               sv[0] = bf16_lo_to_f(a.x); sv[1] = bf16_hi_to_f(a.x); sv[2] = bf16_lo_to_f(a.y); sv[3] = bf16_hi_to_f(a.y);
               sv[4] = bf16_lo_to_f(a.z); sv[5] = bf16_hi_to_f(a.z); sv[6] = bf16_lo_to_f(a.w); sv[7] = bf16_hi_to_f(a.w);
-              if (side_lo && !pre_side) {
+              if (side_lo) {
                 const uint4 b = pl[jj * 2 + hf];
                 sv[0] += bf16_lo_to_f(b.x); sv[1] += bf16_hi_to_f(b.x); sv[2] += bf16_lo_to_f(b.y); sv[3] += bf16_hi_to_f(b.y);
                 sv[4] += bf16_lo_to_f(b.z); sv[5] += bf16_hi_to_f(b.z); sv[6] += bf16_lo_to_f(b.w); sv[7] += bf16_hi_to_f(b.w);

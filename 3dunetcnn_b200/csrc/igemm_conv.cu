@@ -185,50 +185,20 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
           ? (((long long)n * (2 * p.Do) + 2 * d + ((cls >> 2) & 1)) * (2 * p.Ho) + 2 * h + ((cls >> 1) & 1)) * (2 * p.Wo) + 2 * w + (cls & 1)
           : (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
     };
-    // Class mode, single-pass bf16, BN <= 64: the eight class drains are software-pipelined -- the side rows of class c + 1 are
-    // requested before class c is drained (the first ones before the accumulators are even ready), and two staging tiles
-    // alternate so that a class does not wait for the previous class's store to release the tile.  The ncu source view of the
-    // level-0 stride-2 gradient had 20 % of the epilogue warps' samples on the side-row loads and 6 % on the release barriers
-    // (profiles/r02_class_dgrad_ncu.txt).
-    constexpr int NSIDE = (BN < 64 ? BN : 64) / 8;
-    const bf16* side_hi = p.mode == 0 ? p.res_hi : p.x_hi;
-    const int side_ld = p.mode == 0 ? p.ldr : p.ldx;
-    const bool piped = p.cls_mode && !split && BN <= 64 && side_hi != nullptr && Cfg::PIPE_BYTES >= 2 * 128 * BN * 2;
-    uint4 side_nxt[NSIDE];
-    auto load_side_rows = [&](int cls) {
-      const long long vx = vox_of(cls);
-#pragma unroll
-      for (int i = 0; i < NSIDE; ++i) {
-        side_nxt[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (valid && n0 + i * 8 < p.Cout) side_nxt[i] = *reinterpret_cast<const uint4*>(side_hi + vx * side_ld + n0 + i * 8);
-      }
-    };
-    if (piped) load_side_rows(0);
-    else
-      for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) conv_epilogue_prefetch(p, n0, BN, vox_of(cls), valid);   // -> L2 while the MMAs run
-#pragma unroll 1
+    for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) conv_epilogue_prefetch(p, n0, BN, vox_of(cls), valid);   // -> L2 while the MMAs run
     for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
       const long long vox = vox_of(cls);
-      uint8_t* stage = piped ? smem + (cls & 1) * (128 * BN * 2) : smem;
       if (cls == 0) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
         mbar_wait(tfull_bar, 0);
         tc_fence_after();
       } else {
-        // the store that last read this staging tile has released it (piped: the one before the previous class's)
-        if (threadIdx.x == 64) { if (piped) tma_store_wait_read1(); else tma_store_wait_read0(); }
+        if (threadIdx.x == 64) tma_store_wait_read0();    // the previous class's stores have read the staging tile
         asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      uint4 side_cur[NSIDE];
-      if (piped) {
-#pragma unroll
-        for (int i = 0; i < NSIDE; ++i) side_cur[i] = side_nxt[i];
-        if (cls + 1 < 8) load_side_rows(cls + 1);
       }
       // all MMAs have completed (tfull) => every pipeline stage has been consumed: the stage memory is free and is reused
       // as the output staging tile [BN/CBO boxes][128 rows][CBO] (+ lo tile), TMA-stored below
-      conv_epilogue_tile<BN>(p, tmem_base + cls * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, stage, row, split,
-                             piped ? side_cur : nullptr);
+      conv_epilogue_tile<BN>(p, tmem_base + cls * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, row, split);
       fence_proxy_async();
       tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -238,8 +208,8 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
 #pragma unroll
         for (int cb = 0; cb < BN / CBO; ++cb) {
           if (n0 + cb * CBO < p.Cout) {
-            tma_store_5d(mo_hi, stage + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
-            if (split) tma_store_5d(mo_lo, stage + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+            tma_store_5d(mo_hi, smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+            if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
           }
         }
         tma_store_commit();
