@@ -36,6 +36,7 @@ struct ConvArgs {
   int ntaps[2], ksz[2], kchunks[2], stride[2], pad[2];
   int npass;
   int mode;
+  int cls_pair;     // parity-class mode, single-pass bf16: the two W-parity classes share one 256-row staging tile and one dense store
   bf16* out_hi; bf16* out_lo; int ldo;
   const bf16* res_hi; const bf16* res_lo; int ldr;
   const float* scale;

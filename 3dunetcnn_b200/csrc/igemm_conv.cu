@@ -188,28 +188,38 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) conv_epilogue_prefetch(p, n0, BN, vox_of(cls), valid);   // -> L2 while the MMAs run
     for (int cls = 0; cls < (p.cls_mode ? 8 : 1); ++cls) {
       const long long vox = vox_of(cls);
+      // cls_pair: classes (pd, ph, 0) and (pd, ph, 1) interleave along W in ONE staging tile of 256 rows (row = output voxel
+      // (dl, hl, 2 wl + pw) of a box 2 tw wide) that is stored through the dense class-pair map after the second drain
+      const bool pair = p.cls_pair != 0, pair_first = pair && (cls & 1) == 0, pair_second = pair && (cls & 1) == 1;
       if (cls == 0) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats / s_coef initialised
         mbar_wait(tfull_bar, 0);
         tc_fence_after();
-      } else {
-        if (threadIdx.x == 64) tma_store_wait_read0();    // the previous class's stores have read the staging tile
+      } else if (!pair_second) {
+        if (threadIdx.x == 64) tma_store_wait_read0();    // the previous stores have read the staging tile
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      const int srow = pair ? (dl * p.th + hl) * (2 * p.tw) + 2 * wl + (cls & 1) : row;
+      constexpr int SROWS_BOX = 128 * CBO * 2;
       // all MMAs have completed (tfull) => every pipeline stage has been consumed: the stage memory is free and is reused
-      // as the output staging tile [BN/CBO boxes][128 rows][CBO] (+ lo tile), TMA-stored below
-      conv_epilogue_tile<BN>(p, tmem_base + cls * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, row, split);
+      // as the output staging tile [BN/CBO boxes][128 (pair: 256) rows][CBO] (+ lo tile), TMA-stored below
+      conv_epilogue_tile<BN>(p, tmem_base + cls * BN, lane_base, lane, n, n0, vox, valid, s_stats, s_coef, want_stats, edge, smem, srow, split);
+      if (pair_first) continue;     // the other W parity fills the odd rows of the same tile
       fence_proxy_async();
       tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
-        const CUtensorMap* mo_hi = p.cls_mode ? &cmaps.oc[cls][0] : &maps.o[0];
-        const CUtensorMap* mo_lo = p.cls_mode ? &cmaps.oc[cls][1] : &maps.o[1];
+        if (pair) {
+          tma_store_5d(&cmaps.oc[cls & 6][0], smem, n0, 2 * w0, h0, d0, n);
+        } else {
+          const CUtensorMap* mo_hi = p.cls_mode ? &cmaps.oc[cls][0] : &maps.o[0];
+          const CUtensorMap* mo_lo = p.cls_mode ? &cmaps.oc[cls][1] : &maps.o[1];
 #pragma unroll
-        for (int cb = 0; cb < BN / CBO; ++cb) {
-          if (n0 + cb * CBO < p.Cout) {
-            tma_store_5d(mo_hi, smem + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
-            if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * (128 * CBO * 2), n0 + cb * CBO, w0, h0, d0, n);
+          for (int cb = 0; cb < BN / CBO; ++cb) {
+            if (n0 + cb * CBO < p.Cout) {
+              tma_store_5d(mo_hi, smem + cb * SROWS_BOX, n0 + cb * CBO, w0, h0, d0, n);
+              if (split) tma_store_5d(mo_lo, smem + 128 * BN * 2 + cb * SROWS_BOX, n0 + cb * CBO, w0, h0, d0, n);
+            }
           }
         }
         tma_store_commit();
@@ -362,6 +372,15 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
       if (split)
         B200_TRY(make_act_map_class(&cmaps.oc[cls][1], out.lo, out.N, out.D, out.H, out.W, out.C, out.ld, pd, ph, pw, cbo, a.tw,
                                     a.th, a.td, swz_for_bytes(cbo * 2)));
+    }
+    // single-pass bf16: the two W-parity classes of a (pd, ph) pair share one dense store (see tmap.h); the pair maps replace the
+    // even classes' descriptors
+    static const bool no_pair = getenv("B200UNET_CLASS_PAIR") && atoi(getenv("B200UNET_CLASS_PAIR")) == 0;   // A/B switch
+    if (!split && !no_pair) {
+      for (int cls = 0; cls < 8; cls += 2)
+        B200_TRY(make_act_map_classpair(&cmaps.oc[cls][0], out.hi, out.N, out.D, out.H, out.W, out.C, out.ld, (cls >> 2) & 1, (cls >> 1) & 1, cbo,
+                                        2 * a.tw, a.th, a.td, swz_for_bytes(cbo * 2)));
+      a.cls_pair = 1;
     }
     maps.o[0] = cmaps.oc[0][0];   // keeps the (unused) plain output descriptor valid
   } else {

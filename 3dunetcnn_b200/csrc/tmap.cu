@@ -71,6 +71,25 @@ int make_act_map_class(CUtensorMap* out, const bf16* ptr, int N, int D, int H, i
   return OK;
 }
 
+int make_act_map_classpair(CUtensorMap* out, const bf16* ptr, int N, int D, int H, int W, int C, int ld, int pd, int ph, int boxC,
+                           int boxW, int boxH, int boxD, Swz swz) {
+  EncodeTiledFn enc = get_encode();
+  B200_REQUIRE(enc != nullptr, E_DRIVER, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  B200_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, E_INVALID, "class-pair map: extents %dx%dx%d must be even", D, H, W);
+  const bf16* base = ptr + (((long long)pd * H + ph) * W) * ld;
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, E_INVALID, "class-pair map: misaligned view");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)(H / 2), (cuuint64_t)(D / 2), (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)2 * W * ld * 2, (cuuint64_t)2 * H * W * ld * 2, (cuuint64_t)D * H * W * ld * 2};
+  cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxD, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, to_cu(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, E_DRIVER, "cuTensorMapEncodeTiled(class pair) failed: %d (N%d D%d H%d W%d C%d ld%d p%d%d)", (int)r, N, D,
+               H, W, C, ld, pd, ph);
+  return OK;
+}
+
 int make_w_map(CUtensorMap* out, const bf16* ptr, int T, int R, int K, int boxK, int boxR, Swz swz, int boxT) {
   EncodeTiledFn enc = get_encode();
   B200_REQUIRE(enc != nullptr, E_DRIVER, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
