@@ -120,6 +120,10 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200unet_plan_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                          C.c_void_p, C.c_void_p]),
+    "b200unet_plan_backward_parts": (C.c_int, [C.c_void_p]),
+    "b200unet_plan_param_backward_part": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200unet_plan_backward_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.c_void_p, C.c_void_p]),
     "b200unet_plan_last_launches": (C.c_int, [C.c_void_p]),
     "b200unet_plan_algorithmic_macs": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "b200unet_plan_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),

@@ -196,6 +196,16 @@ int b200unet_plan_forward(b200unet_plan* plan, const float* x, const float* cons
 /* backward: dlogits NCDHW fp32 -> grads[i] (fp32, same shapes as params; overwritten). */
 int b200unet_plan_backward(b200unet_plan* plan, const float* dlogits, const float* const* params, float* const* grads,
                            void* workspace, void* stream);
+/* The same backward in two calls, so that a data-parallel caller can exchange the gradients that are already final while the
+ * rest of the backward runs (the reference's DataParallel reduces every gradient after the whole backward:
+ * unet3d/models/build.py:18-20).  backward_parts: 2 when the schedule has a split point (part 0 = head, decoder, deepest
+ * encoder level(s): most of the parameters; part 1 = the shallow encoder levels), 1 otherwise, 0 for an inference_only plan.
+ * param_backward_part(i): the part after which grads[i] is final.  backward_part(0) followed by backward_part(1) on the same
+ * stream writes exactly what b200unet_plan_backward writes; both calls take the same pointers. */
+int b200unet_plan_backward_parts(const b200unet_plan* plan);
+int b200unet_plan_param_backward_part(const b200unet_plan* plan, int i);
+int b200unet_plan_backward_part(b200unet_plan* plan, int part, const float* dlogits, const float* const* params, float* const* grads,
+                                void* workspace, void* stream);
 /* number of kernels the last forward / backward call launched (for bench.py's gpu_launches) */
 int b200unet_plan_last_launches(const b200unet_plan* plan);
 

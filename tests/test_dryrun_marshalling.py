@@ -13,6 +13,7 @@ import torch
 
 HOST_ONLY = {"b200unet_version", "b200unet_last_error", "b200unet_plan_create", "b200unet_plan_destroy", "b200unet_plan_num_params",
              "b200unet_plan_param_info", "b200unet_plan_workspace_bytes", "b200unet_plan_last_launches", "b200unet_plan_algorithmic_macs",
+             "b200unet_plan_backward_parts", "b200unet_plan_param_backward_part",
              "b200unet_head_bwd_scratch_bytes"}
 
 

@@ -43,8 +43,28 @@ def _worker(rank, world, port, q):
     sync2 = par.GradAllReduce(qs, model=model)
     sync2()
     assert [q_.grad.data_ptr() for q_ in qs] == ptrs and sync2.flat is None      # reduced in place, no staging buffer
+    # overlapped exchange: begin() reduces the early slice (what part 0 of the backward has finished), the caller runs the rest of
+    # the backward (here: writes the late slice), finish() reduces the late slice
+    class TwoPart(Bucketed):
+        split = 8
+
+        def flat_gradient_bucket_parts(self):
+            return self.bucket[:self.split], self.bucket[self.split:]
+    qs3 = [torch.nn.Parameter(torch.zeros(4, 2)), torch.nn.Parameter(torch.zeros(3))]
+    m3 = TwoPart(qs3)
+    sync3 = par.GradAllReduce(qs3, model=m3)
+    assert sync3.supports_overlap and not sync2.supports_overlap          # sync2's model has no two-part bucket
+    m3.bucket[:8] = float(rank + 1)
+    m3.bucket[8:] = float("nan")                                          # "not computed yet": begin() must not touch it
+    sync3.begin()
+    early_after_begin = m3.bucket[:8].clone()
+    late_untouched = bool(torch.isnan(m3.bucket[8:]).all())
+    m3.bucket[8:] = float(100 * (rank + 1))                                # part 1 of the backward
+    sync3.finish()
+    sync3.finish()                                                         # without a begin(): the plain whole-bucket exchange
     out = {"p0": params[0].detach().clone(), "g0": params[0].grad.clone(), "g1": params[1].grad.clone(),
-           "shard": list(par.shard_batch(7, rank, world)), "bucket": model.bucket.clone()}
+           "shard": list(par.shard_batch(7, rank, world)), "bucket": model.bucket.clone(),
+           "early_after_begin": early_after_begin, "late_untouched": late_untouched, "bucket3": m3.bucket.clone()}
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -68,6 +88,8 @@ def test_grad_allreduce_and_sharding_world2():
     assert res[0]["shard"] == [0, 1, 2, 3] and res[1]["shard"] == [4, 5, 6]
     for r in (0, 1):
         assert torch.allclose(res[r]["bucket"], torch.full((11,), 15.0))  # mean of 10 and 20, in the bucket itself
+        assert torch.allclose(res[r]["early_after_begin"], torch.full((8,), 1.5)) and res[r]["late_untouched"]
+        assert torch.allclose(res[r]["bucket3"], torch.cat([torch.full((8,), 1.5), torch.full((3,), 150.0)]))
 
 
 def test_single_process_is_a_noop():
