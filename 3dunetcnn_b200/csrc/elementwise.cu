@@ -611,7 +611,9 @@ int launch_act_bwd(const Act& g1, const Act* g2, const Act& c, const float* coef
 }
 
 // dbias[o] = sum over n, voxels of dlogits[n][o][s]   (bias of the 1x1x1 output block, MONAI UnetOutBlock)
-__global__ void k_head_dbias(const float* __restrict__ dlogits, int N, int NO, long long S, float* __restrict__ dbias) {
+// Two launches, no floating-point atomics: per-block fp64 partial sums into `part` [NO][blocks], then one thread per output adds
+// them in a fixed order (a float atomicAdd per block made this the one run-to-run varying gradient of a deterministic plan).
+__global__ void k_head_dbias(const float* __restrict__ dlogits, int N, int NO, long long S, double* __restrict__ part) {
   __shared__ double sh[32];
   const int o = blockIdx.y;
   double acc = 0;
@@ -627,15 +629,27 @@ __global__ void k_head_dbias(const float* __restrict__ dlogits, int N, int NO, l
   if (threadIdx.x == 0) {
     double t = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
-    atomicAdd(&dbias[o], (float)t);
+    part[(size_t)o * gridDim.x + blockIdx.x] = t;
   }
 }
 
-int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st) {
-  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * NO, st));
+__global__ void k_head_dbias_sum(const double* __restrict__ part, int blocks, int NO, float* __restrict__ dbias) {
+  const int o = threadIdx.x;
+  if (o >= NO) return;
+  double t = 0;
+  for (int i = 0; i < blocks; ++i) t += part[(size_t)o * blocks + i];
+  dbias[o] = (float)t;
+}
+
+// scratch: >= 128 * NO doubles (the head's weight-gradient slot arena, head_bwd_scratch_bytes(), is free again by now)
+int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st, float* scratch) {
+  B200_REQUIRE(scratch != nullptr && NO >= 1 && NO <= 32, E_INVALID, "head_dbias: needs scratch, 1 <= n_outputs <= 32");
   long long want = (S + 255) / 256;
   const int blocks = (int)(want < 128 ? (want > 0 ? want : 1) : 128);
-  k_head_dbias<<<dim3(blocks, NO), 256, 0, st>>>(dlogits, N, NO, S, dbias);
+  double* part = reinterpret_cast<double*>(scratch);
+  k_head_dbias<<<dim3(blocks, NO), 256, 0, st>>>(dlogits, N, NO, S, part);
+  B200_CHECK_CUDA(cudaGetLastError());
+  k_head_dbias_sum<<<1, 32, 0, st>>>(part, blocks, NO, dbias);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -26,7 +26,7 @@ bool use_tiled_upsample_bwd();
 int launch_upsample2x_bwd_tiled(const Act& dy, const Act& dx, cudaStream_t st);
 int launch_head_fwd(const Act& x, const float* w, int n_out, int act_mode, float* logits, cudaStream_t st,
                     const float* bias = nullptr);
-int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st);
+int launch_head_dbias(const float* dlogits, int N, int NO, long long S, float* dbias, cudaStream_t st, float* scratch);
 // post-activation blocks: dz = (g1 [+ g2]) * act'(A c + B), bstats += (sum dz, sum dz*xhat)
 int launch_act_bwd(const Act& g1, const Act* g2, const Act& c, const float* coef, float slope, const Act& dz, double* bstats,
                    int bstats_ld, cudaStream_t st);

@@ -1138,7 +1138,8 @@ static int build_dynunet(Plan& P) {
       LAUNCHED(cx, CAT_HEAD, launch_head_bwd(act_of(P, cx, Xfinal), cx.params[P.head_param], P.d.n_outputs, cx.dlogits, act_of(P, cx, gg),
                                              cx.grads[P.head_param], cx.st, reinterpret_cast<float*>(cx.ws + P.head_part_off)));
       const Buf& b = P.bufs[Xfinal.buf];
-      LAUNCHED(cx, CAT_HEAD, launch_head_dbias(cx.dlogits, b.N, P.d.n_outputs, (long long)b.D * b.H * b.W, cx.grads[head_bias], cx.st));
+      LAUNCHED(cx, CAT_HEAD, launch_head_dbias(cx.dlogits, b.N, P.d.n_outputs, (long long)b.D * b.H * b.W, cx.grads[head_bias], cx.st,
+                                               reinterpret_cast<float*>(cx.ws + P.head_part_off)));
       return OK;
     });
   }

@@ -209,6 +209,11 @@ def test_two_part_backward_is_the_whole_backward(pkg, arch):
     parts = model.flat_gradient_bucket_parts()
     assert parts is not None and parts[0].numel() > parts[1].numel() > 0          # most parameters are final early
     assert parts[0].numel() + parts[1].numel() == whole.numel()
+    for p in model.parameters():
+        p.grad = None
+    crit(model(x), t).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(model.flat_gradient_bucket(), whole), "a deterministic plan must repeat its gradients bit for bit"
     # two parts; poison the bucket first so that a gradient nobody writes shows up
     for p in model.parameters():
         p.grad = None
