@@ -66,8 +66,9 @@ class GraphedTrainStep:
     0-dim tensor (read it with ``.item()`` when needed).  The model runs in flat-gradient mode: every replay overwrites
     the ``.grad`` views of one persistent bucket, which ``grad_sync`` all-reduces in place.
 
-    ``split_backward`` (default: on when ``grad_sync`` can overlap, i.e. a ``parallel.GradAllReduce`` over NCCL; off with
-    ``B200UNET_OVERLAP_ALLREDUCE=0``): the step is captured as TWO graphs around the schedule's split point -- forward + loss +
+    ``split_backward`` (default off; ``B200UNET_OVERLAP_ALLREDUCE=1`` turns it on wherever ``grad_sync`` can overlap, i.e. a
+    ``parallel.GradAllReduce`` with more than one rank -- measured neutral on two B200s, profiles/r02_overlap_ab.txt, so the
+    one-graph step stays the default): the step is captured as TWO graphs around the schedule's split point -- forward + loss +
     backward of head / decoder / deepest encoder level, then the backward of the shallow encoder levels.  Between the two
     replays ``grad_sync.begin()`` starts the all-reduce of the first ~90 % of the bucket on a side stream, so the exchange runs
     under the second graph; ``grad_sync.finish()`` reduces the small remainder (bucketed, overlapped exchange; the
@@ -79,7 +80,7 @@ class GraphedTrainStep:
         self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
         if split_backward is None:
             split_backward = (grad_sync is not None and bool(getattr(grad_sync, "supports_overlap", False))
-                              and os.environ.get("B200UNET_OVERLAP_ALLREDUCE", "1") != "0")
+                              and os.environ.get("B200UNET_OVERLAP_ALLREDUCE", "0") == "1")
         self.split_backward = bool(split_backward)
         self.graph_tail = None
         device = device or next(model.parameters()).device

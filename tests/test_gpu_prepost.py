@@ -245,8 +245,8 @@ def test_graphed_train_step_split_backward_matches_single_graph(pkg):
         crit = pkg.DiceLoss(sigmoid=True)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)
         sync = _RecordingSync(model) if mode == "split" else None
-        step = pkg.train.GraphedTrainStep(model, crit, opt, (2, 2, 16, 16, 16), (2, 2, 16, 16, 16), grad_sync=sync)
-        assert step.split_backward == (mode == "split")
+        step = pkg.train.GraphedTrainStep(model, crit, opt, (2, 2, 16, 16, 16), (2, 2, 16, 16, 16), grad_sync=sync,
+                                          split_backward=(mode == "split"))
         losses = []
         for i in range(4):
             x, t = _batch(100 + i)
