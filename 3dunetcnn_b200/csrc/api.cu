@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <cstdlib>
 #include "kernels.h"
 #include "../../include/b200unet.h"
 #include "../../include/b200unet_diag.h"
@@ -15,6 +16,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// opt-in until measured on B200 in both states (common.cuh: launch_pdl)
+static const bool kPdlDefault = false;
+bool pdl_enabled() {
+  static const bool on = getenv("B200UNET_PDL") ? atoi(getenv("B200UNET_PDL")) != 0 : kPdlDefault;
+  return on;
+}
 
 static Act to_act(const b200unet_tensor* t) {
   return make_act(reinterpret_cast<bf16*>(t->hi), reinterpret_cast<bf16*>(t->lo), t->n, t->d, t->h, t->w, t->c, t->ld);

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -56,6 +57,30 @@ static inline Act make_act(bf16* hi, bf16* lo, int N, int D, int H, int W, int C
 static inline Act slice_c(const Act& a, int c0, int c) {
   Act r = a; r.hi = a.hi + c0; r.lo = a.lo ? a.lo + c0 : nullptr; r.C = c; return r;
 }
+
+// Programmatic dependent launch (opt-in: B200UNET_PDL=1).  A kernel launched through launch_pdl may be scheduled while the previous
+// kernel of the stream still runs: its CTAs take SMs as that kernel's CTAs retire, run their set-up (barrier init, TMEM
+// allocation, descriptor prefetch) and block in pdl_wait() (ptx.cuh) until the previous kernel has completed and its writes are
+// visible -- the launch latency and the set-up of every launch leave the critical path.  ONLY kernels that execute pdl_wait()
+// before their first access to global memory may be launched this way.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (!pdl_enabled()) {
+    kernel<<<grid, block, smem, st>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, args...);   // the caller checks cudaGetLastError() as after a <<<>>> launch
+}
+#endif
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

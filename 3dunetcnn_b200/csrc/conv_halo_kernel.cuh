@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(NI == 2 ? 384 : 352, 1) k_conv_halo(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlapped the tail of the previous kernel; nothing below may
+  pdl_launch_dependents();
 
   // K groups of one tile: source 0 = 27 taps per chunk (9 stages of TPB taps when TPB = 3), source 1 (optional
   // 1x1x1) = its centre tap per chunk
@@ -743,7 +745,7 @@ static int launch_halo_cfg(const ConvMaps& maps, const ConvArgs& a, HaloArgs h, 
     B200_CHECK_CUDA(cudaFuncSetAttribute(k_conv_halo<KC, BN, TD, NI, KW, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[dev] = true;
   }
-  k_conv_halo<KC, BN, TD, NI, KW, EV><<<grid, NI == 2 ? 384 : 352, smem_bytes, st>>>(maps, a, h);
+  launch_pdl(k_conv_halo<KC, BN, TD, NI, KW, EV>, dim3(grid), dim3(NI == 2 ? 384 : 352), smem_bytes, st, maps, a, h);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -204,6 +204,8 @@ struct GnFin {
 };
 template <bool FUSED>
 __global__ void __launch_bounds__(256) k_gn_apply(Act x, Act y, const float4* __restrict__ coef, float slope, GnFin f) {
+  pdl_wait();                 // launched through launch_pdl: the producer of x / of the statistics has completed past this line
+  pdl_launch_dependents();
   const int c8n = x.C / 8;
   const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
@@ -301,11 +303,11 @@ static int launch_gn_apply_impl(const Act& x, const Act& y, const float* coef, f
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   if (fin) {
     B200_REQUIRE(x.C <= 1024, E_UNSUPPORTED, "gn_apply: fused finalize supports C <= 1024 (got %d)", x.C);
-    k_gn_apply<true><<<dim3(blocks, x.N), threads, 0, st>>>(x, y, nullptr, slope, *fin);
+    launch_pdl(k_gn_apply<true>, dim3(blocks, x.N), dim3(threads), 0, st, x, y, (const float4*)nullptr, slope, *fin);
   } else {
     GnFin none;
     memset(&none, 0, sizeof(none));
-    k_gn_apply<false><<<dim3(blocks, x.N), threads, 0, st>>>(x, y, reinterpret_cast<const float4*>(coef), slope, none);
+    launch_pdl(k_gn_apply<false>, dim3(blocks, x.N), dim3(threads), 0, st, x, y, reinterpret_cast<const float4*>(coef), slope, none);
   }
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
@@ -399,6 +401,8 @@ template <bool FUSED>
 __global__ void __launch_bounds__(256) k_gn_bwd(Act dz, Act x, const float4* __restrict__ coef,
                                                 const float2* __restrict__ coef2, Act add1, Act add2, Act dx,
                                                 const float* __restrict__ scale, GnBwdFin f) {
+  pdl_wait();                 // launched through launch_pdl
+  pdl_launch_dependents();
   const int c8n = x.C / 8;
   const int n = blockIdx.y;
   const long long S = (long long)x.D * x.H * x.W;
@@ -511,14 +515,13 @@ static int launch_gn_bwd_impl(const Act& dz, const Act& x, const float* coef, co
   int blocks = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   if (fin) {
     B200_REQUIRE(x.C <= 1024, E_UNSUPPORTED, "gn_bwd: fused finalize supports C <= 1024 (got %d)", x.C);
-    k_gn_bwd<true><<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef), nullptr,
-                                                          add1 ? *add1 : none, add2 ? *add2 : none, dx, scale, *fin);
+    launch_pdl(k_gn_bwd<true>, dim3(blocks, x.N), dim3(threads), 0, st, dz, x, reinterpret_cast<const float4*>(coef), (const float2*)nullptr,
+               add1 ? *add1 : none, add2 ? *add2 : none, dx, scale, *fin);
   } else {
     GnBwdFin nofin;
     memset(&nofin, 0, sizeof(nofin));
-    k_gn_bwd<false><<<dim3(blocks, x.N), threads, 0, st>>>(dz, x, reinterpret_cast<const float4*>(coef),
-                                                           reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none,
-                                                           add2 ? *add2 : none, dx, scale, nofin);
+    launch_pdl(k_gn_bwd<false>, dim3(blocks, x.N), dim3(threads), 0, st, dz, x, reinterpret_cast<const float4*>(coef),
+               reinterpret_cast<const float2*>(coef2), add1 ? *add1 : none, add2 ? *add2 : none, dx, scale, nofin);
   }
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;

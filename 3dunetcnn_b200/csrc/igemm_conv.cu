@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
     tmem_alloc(tmem_slot, p.cls_mode ? (8 * BN < 32 ? 32 : 8 * BN) : Cfg::TMEM_COLS);   // class mode: one accumulator per parity class
     tmem_relinquish();
   }
+  pdl_wait();   // before the first global read (the coefficient table below); barrier init / TMEM allocation above overlap the previous kernel
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
     for (int i = e; i < 4 * BN * 2; i += 128) s_stats[i] = 0.f;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ Conv
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   // class mode: ONE CTA computes all eight parity classes of its voxel tile (27 tap products walked class by class into
   // eight TMEM accumulators, then eight tile stores).  One CTA per class spent most of its life in set-up: 32768 CTAs of
@@ -260,7 +262,7 @@ static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cud
                                          Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  k_igemm_conv<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, args, cmaps);
+  launch_pdl(k_igemm_conv<BN, KC>, grid, dim3(192), Cfg::SMEM_BYTES, st, maps, args, cmaps);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -150,6 +150,13 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
                "r"(ncols)
                : "memory");
 }
+// Programmatic dependent launch (common.cuh: launch_pdl).  pdl_wait: returns once the preceding kernel of the stream has completed
+// and its memory operations are visible (immediately when this grid was not launched with the attribute).
+// pdl_launch_dependents: this CTA no longer holds back the launch of the NEXT kernel; issued after the TMEM allocation so that a
+// dependent CTA that becomes resident beside this one can never take TMEM columns this CTA still has to allocate.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_relinquish() {
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(192) k_wgrad(const __grid_constant__ WgradMaps
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // set-up above overlaps the tail of the previous kernel; no global access before this line
+  pdl_launch_dependents();
   const int pad = p.pad;
 
   if (warp == 0) {
@@ -244,7 +246,7 @@ static int launch_wg(const WgradMaps& maps, const WgradArgs& a, dim3 grid, cudaS
     B200_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (dev < 64) attr_set[dev] = true;
   }
-  k_wgrad<CB, BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a);
+  launch_pdl(k_wgrad<CB, BN>, grid, dim3(192), Cfg::SMEM_BYTES, st, maps, a);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // set-up above overlaps the tail of the previous kernel; no global access before this line
+  pdl_launch_dependents();
   if (warp >= 2) {   // zero this warp's lane quadrant of every accumulator column
     for (int c = 0; c < nq * 3 * BN; c += 16) tmem_zero16(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c);
     tmem_st_wait();
@@ -242,7 +244,7 @@ static int launch_wgh(const WgHaloMaps& maps, const WgHaloArgs& a, dim3 grid, cu
                                          Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  k_wgrad_halo<KC, BN, TD><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, a);
+  launch_pdl(k_wgrad_halo<KC, BN, TD>, grid, dim3(192), Cfg::SMEM_BYTES, st, maps, a);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
