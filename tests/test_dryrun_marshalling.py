@@ -115,6 +115,44 @@ def test_flat_gradient_bucket_binding(pkg, stubbed):
     assert [p.grad.data_ptr() for p in model.parameters()] == first
     sync = pkg.parallel.GradAllReduce(model.parameters(), model=model)
     sync()                                   # no process group: a no-op that must not raise
+    # bucket layout: the parameters whose gradients part 0 of the two-part backward finishes (head, decoder, deepest encoder level)
+    # form the leading slice, state-dict order within each slice; the views themselves stay in state-dict order
+    early, late = model.flat_gradient_bucket_parts()
+    assert early.data_ptr() == bucket.data_ptr() and early.numel() + late.numel() == bucket.numel() and late.numel() > 0
+    plan = next(iter(model._plans.values()))
+    parts = plan.param_parts()
+    split = bucket.data_ptr() + 4 * early.numel()
+    offs = {0: [], 1: []}
+    for p, part in zip(model.ordered_parameters(), parts):
+        assert (p.grad.data_ptr() < split) == (part == 0)
+        offs[part].append(p.grad.data_ptr())
+    assert offs[0] == sorted(offs[0]) and offs[1] == sorted(offs[1])
+    assert not sync.supports_overlap and not sync._begun      # single process: begin() declines, finish() is the plain call
+    sync.begin()
+    sync.finish()
+
+
+def test_deferred_backward_tail_calls(pkg, stubbed):
+    """two-part backward marshalling: with the tail deferred the autograd backward issues part 0 only, finish_backward() part 1"""
+    model = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8)
+    model.train()
+    model.use_flat_gradients(True)
+    x, _ = _batch()
+    model._defer_backward_tail = True
+    model(x).sum().backward()
+    model._defer_backward_tail = False
+    assert stubbed.count("b200unet_plan_backward_part") == 1 and stubbed.count("b200unet_plan_backward") == 0
+    assert model._backward_tail is not None
+    model.finish_backward()
+    assert stubbed.count("b200unet_plan_backward_part") == 2 and model._backward_tail is None
+    with pytest.raises(RuntimeError, match="no deferred backward"):
+        model.finish_backward()
+    # without the flat bucket the gradients go back through autograd: the backward cannot be deferred
+    model2 = pkg.UNet3D(n_features=4, n_outputs=3, base_width=8)
+    model2.train()
+    model2._defer_backward_tail = True
+    model2(x).sum().backward()
+    assert model2._backward_tail is None and stubbed.count("b200unet_plan_backward") == 1
 
 
 def test_dynunet_calls(pkg, stubbed):
