@@ -23,13 +23,17 @@
 
 namespace b200 {
 
-template <int BN, int KC>
+// DEEP: the pipeline ring takes ~196 KB instead of 96 KB.  The 96 KB ring lets two CTAs share an SM (192 KB of loads in flight per
+// SM); a launch with no more CTAs than SMs has one CTA per SM whatever it allocates, and with three 32 KB stages in flight it is
+// bound by the L2 round trip (the 256-channel layers at 16^3: ~34 B/clk per SM, profiles/r02_layer_times.csv) -- those launches
+// take the deep ring.
+template <int BN, int KC, int DEEP = 0>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_BOX_BYTES = BN * KC * 2;
   static constexpr int B_BYTES = B_BOX_BYTES < 1024 ? 1024 : B_BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = ((DEEP ? 196 : 96) * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 2 * 4 + BN * 16;  // barriers+slot | per-warp stats | coef
@@ -40,10 +44,10 @@ struct ConvCfg {
   static constexpr uint32_t SBO = 8 * KC * 2;
 };
 
-template <int BN, int KC>
+template <int BN, int KC, int DEEP>
 __global__ void __launch_bounds__(192) k_igemm_conv(const __grid_constant__ ConvMaps maps, const ConvArgs p,
                                                     const __grid_constant__ ConvClassMaps cmaps) {
-  using Cfg = ConvCfg<BN, KC>;
+  using Cfg = ConvCfg<BN, KC, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space and every
   // shared-memory access below would compile to a generic LD.E / ST.E (ncu source view, round 2) instead of LDS / STS
@@ -251,21 +255,23 @@ static void pick_tile(int Wo, int Ho, int Do, int& tw, int& th, int& td) {
   td = rem / th;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int DEEP = 0>
 static int launch_cfg(const ConvMaps& maps, const ConvArgs& args, dim3 grid, cudaStream_t st, const ConvClassMaps& cmaps) {
-  using Cfg = ConvCfg<BN, KC>;
+  using Cfg = ConvCfg<BN, KC, DEEP>;
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(k_igemm_conv<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k_igemm_conv<BN, KC, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  launch_pdl(k_igemm_conv<BN, KC>, grid, dim3(192), Cfg::SMEM_BYTES, st, maps, args, cmaps);
+  launch_pdl(k_igemm_conv<BN, KC, DEEP>, grid, dim3(192), Cfg::SMEM_BYTES, st, maps, args, cmaps);
   B200_CHECK_CUDA(cudaGetLastError());
   return OK;
 }
+
+static const int kIgemmDeepDefault = 0;   // opt-in until measured (B200UNET_IGEMM_DEEP=1)
 
 static int sm_count() {
   static int cached[64] = {0};
@@ -408,6 +414,12 @@ int launch_igemm_conv_streaming(const ConvOp& op, cudaStream_t st) {
     a.slope = op.slope; a.bstats = op.bstats;
   }
   dim3 grid((unsigned)((long long)a.N * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)ceil_div(out.C, BN), 1u);
+  // at most one CTA per SM: nothing is lost by taking the whole shared memory for a deeper ring (see ConvCfg); only the 64-channel
+  // K chunks have stages large enough for the 96 KB budget to cap the ring below six
+  static const int deep_env = getenv("B200UNET_IGEMM_DEEP") ? atoi(getenv("B200UNET_IGEMM_DEEP")) : kIgemmDeepDefault;
+  const bool deep = deep_env != 0 && !op.cls_mode && KC == 64 && (long long)grid.x * grid.y <= sm_count();
+  if (deep && BN == 128) return launch_cfg<128, 64, 1>(maps, a, grid, st, cmaps);
+  if (deep && BN == 64) return launch_cfg<64, 64, 1>(maps, a, grid, st, cmaps);
 #define B200_CONV_CASE(bn, kc) \
   if (BN == bn && KC == kc) return launch_cfg<bn, kc>(maps, a, grid, st, cmaps);
   B200_CONV_CASE(16, 16) B200_CONV_CASE(16, 32) B200_CONV_CASE(16, 64)
