@@ -113,3 +113,22 @@ def test_two_part_backward_assigns_every_parameter(pkg):
     assert dplan.backward_parts() == 2
     assert all(v == 0 for k, v in dparts.items() if k.startswith(("upsamples.", "bottleneck.", "output_block.", "downsamples.3.")))
     assert all(v == 1 for k, v in dparts.items() if k.startswith(("input_block.", "downsamples.0.", "downsamples.1.", "downsamples.2.")))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_features=1, n_outputs=1, base_width=16, encoder_blocks=[1, 2, 2, 4, 4]),
+    dict(n_features=4, n_outputs=3, base_width=8, use_transposed_convolutions=True),
+    dict(n_features=2, n_outputs=2, base_width=8, encoder_blocks=[1, 1], decoder_blocks=[1, 1]),
+    dict(n_features=4, n_outputs=3, base_width=8, decoder_mirrors_encoder=True),
+])
+def test_two_part_backward_split_follows_the_architecture(pkg, kw):
+    """Whatever the depth / decoder flavour: exactly the shallow encoder levels (and the stride-2 convolutions below the deepest
+    one) belong to part 1; everything the backward reaches earlier -- head, decoder incl. transposed-convolution weights AND
+    biases, deepest encoder level, the stride-2 convolution feeding it -- is final after part 0."""
+    net, plan = _plan(pkg, 1, 32, 32, 32, **kw)
+    levels = len(kw.get("encoder_blocks", [1, 2, 2, 4]))
+    assert plan.backward_parts() == 2
+    for (key, _), part in zip(plan.param_spec(), plan.param_parts()):
+        late = any(key.startswith("encoder.layers.%d." % i) for i in range(levels - 1)) or \
+            any(key.startswith("encoder.downsampling_convolutions.%d." % i) for i in range(levels - 2))
+        assert part == (1 if late else 0), (key, part)
